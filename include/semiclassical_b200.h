@@ -1,0 +1,162 @@
+/*
+ * semiclassical_b200.h -- C ABI of the B200-native semiclassical propagation engine.
+ *
+ * Drop-in boundary for the hot path of humeniuka/semiclassical's `semi dynamics` task.  The reference has
+ * no FFI layer (it is pure Python/torch); the "interface each entry point replaces" is therefore the
+ * duck-typed Python protocol of semiclassical/propagators.py and semiclassical/potentials.py.  Every entry
+ * point cites the reference method(s) whose numerics it replaces.  The Python host mirror
+ * (semiclassical_b200/propagators.py, potentials.py) binds these symbols with ctypes; INTEGRATION.md
+ * shows the same stub applied to the reference package itself.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns an int status (SC_OK == 0); sc_last_error() gives the message
+ *   - "_dev" pointers are CUDA device pointers (e.g. tensor.data_ptr()), "_host" pointers are host memory
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - real arrays are fp64, complex arrays are interleaved (re, im) fp64 pairs ("c128")
+ *   - ensemble arrays use the reference's batch-last layout: zi is (2d, n), y is (2d+4d^2+1, n),
+ *     trajectory index contiguous (propagators.py:329-334, 581-603)
+ *   - matrices are row-major
+ */
+#ifndef SEMICLASSICAL_B200_H
+#define SEMICLASSICAL_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SC_OK 0
+#define SC_ERR_INVALID 1      /* bad argument / wrong call order  -> AssertionError in the Python mirror */
+#define SC_ERR_CUDA 2         /* CUDA runtime failure             -> RuntimeError */
+#define SC_ERR_UNSUPPORTED 3  /* configuration outside the kernels' envelope -> NotImplementedError */
+
+#define SC_ABI_VERSION 1
+#define SC_MAX_DIM 64         /* largest number of degrees of freedom the fused kernels accept */
+
+typedef struct sc_potential sc_potential; /* opaque: device-resident potential parameters */
+typedef struct sc_engine sc_engine;       /* opaque: one propagator instance (ensemble + constants) on one GPU */
+
+int sc_abi_version(void);
+const char *sc_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Potentials: batched energy / gradient / Hessian ("harmonic_approximation") and constant NAC vectors.
+ * All constructor arguments are HOST pointers; parameters are copied to the current CUDA device.
+ * --------------------------------------------------------------------------------------------- */
+
+/* MorsePotential(omega, chi, nac): potentials.py:229-327.  a = sqrt(2 omega chi), D = omega/(4 chi) are
+ * computed by the caller exactly as potentials.py:243-255 does (including the chi==0 -> 1e-4 bump);
+ * all_harmonic selects the pure-harmonic branch (potentials.py:267-272).  masses == 1. */
+int sc_potential_create_morse(sc_potential **out, int d, const double *omega_host, const double *a_host,
+                              const double *D_host, int all_harmonic, const double *nac_host);
+
+/* Morse potential in rotated coordinates x = Q r (dense Hessian Q h Q^T, dense-path fixture of SURVEY 8c-vi);
+ * nac_host is the NAC vector in the ROTATED frame (Q tau1). */
+int sc_potential_create_rotated_morse(sc_potential **out, int d, const double *omega_host, const double *a_host,
+                                      const double *D_host, int all_harmonic, const double *nac_host,
+                                      const double *Q_host);
+
+/* NonHarmonicPotential(eps, b): potentials.py:25-205 (1-D Herman-Kluk test potential per mode, tau1 = 1) */
+int sc_potential_create_nonharmonic(sc_potential **out, int d, const double *eps_host, const double *b_host);
+
+/* MolecularHarmonicPotential: potentials.py:529-638.  V = energy0 - origin + g0.dr + dr.H0.dr/2 */
+int sc_potential_create_harmonic(sc_potential **out, int d, const double *pos0_host, double energy0,
+                                 const double *grad0_host, const double *hess0_host, const double *masses_host,
+                                 const double *nac_host);
+
+/* MolecularGDMLPotential / GDMLPredict: potentials.py:641-744, gdml_predictor.py:35-250.
+ * xs_train, jx_alphas: (n_train_expanded, n_desc) row-major, already expanded over permutations
+ * (gdml_predictor.py:67-82). */
+int sc_potential_create_gdml(sc_potential **out, int n_atoms, int n_train, int n_desc, const double *xs_train_host,
+                             const double *jx_alphas_host, double sig, double c, double std,
+                             const double *masses_host, const double *nac_host);
+
+/* energy origin subtracted from V (set by minimize(): potentials.py:523-526, 593, 699) */
+int sc_potential_set_origin(sc_potential *pot, double origin);
+int sc_potential_dimensions(const sc_potential *pot);
+int sc_potential_destroy(sc_potential *pot);
+
+/* potential.harmonic_approximation(r): r_dev (d, n) -> V_dev (n), grad_dev (d, n), hess_dev (d, d, n).
+ * grad_dev / hess_dev may be NULL (energy only / energy+gradient). */
+int sc_potential_eval(const sc_potential *pot, int n, const double *r_dev, double *V_dev, double *grad_dev,
+                      double *hess_dev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Propagator engine
+ * --------------------------------------------------------------------------------------------- */
+
+/* Host-side constants derived from Gamma_i, Gamma_t, Gamma_0, q0, p0 exactly as the reference does in
+ * HermanKlukPropagator.__init__/initial_conditions/_prepare (propagators.py:408-443, 493-531, 633-643)
+ * and WaltonManolopoulosPropagator._prepare (propagators.py:1102-1130). All HOST pointers, copied. */
+typedef struct {
+  int d;                 /* degrees of freedom */
+  int dr;                /* rank of Gamma_i + Gamma_0 (d' in SURVEY.md) */
+  int wm;                /* 0 = Herman-Kluk, 1 = Walton-Manolopoulos */
+  /* prefactor factors with the subspace projection folded in (propagators.py:969-994):
+   * L1 = U^T sqrt(Gamma_t), L2 = U^T Gamma_t^{-1/2}  (dr x d);  R1 = Gamma_i^{-1/2} U, R2 = sqrt(Gamma_i) U (d x dr) */
+  const double *L1, *L2, *R1, *R2;
+  const double *U;       /* d x dr, eigenvectors spanning the non-zero subspace (propagators.py:498) */
+  const double *q0, *p0; /* centre of the initial wavepacket */
+  /* coherent-state overlap constants (propagators.py:160-179, 230): A = Gi iGij Gj, B = iGij, C = Gj iGij, fac */
+  const double *oi0_A, *oi0_B, *oi0_C; double oi0_fac;   /* <qi,pi,Gamma_i | q0,p0,Gamma_0> */
+  const double *ot0_A, *ot0_B, *ot0_C; double ot0_fac;   /* <qt,pt,Gamma_t | q0,p0,Gamma_0> */
+  const double *Gamma_0, *Gamma_i, *Gamma_t, *iGi0;       /* d x d */
+  /* WM only */
+  double alpha, beta;
+  const double *iGamma_0;
+  double detG0, detGi, detGt, detGi0;                     /* pi-absorbed pseudo-determinants (:1117-1125) */
+} sc_engine_config;
+
+int sc_engine_create(sc_engine **out, const sc_engine_config *cfg);
+int sc_engine_destroy(sc_engine *eng);
+
+/* initial_conditions() after sampling (propagators.py:581-631): installs the ensemble (zi, probi), sets
+ * Mqq = Mpp = 1, S = 0, t = 0, evaluates the prefactor once (initialises the sqrt branch trackers).
+ * ntraj_norm is the N of the Monte-Carlo weight 1/(N probi (2 pi hbar)^d) -- the GLOBAL ensemble size when the
+ * ensemble is sharded over ranks (propagators.py:837, 909). */
+int sc_engine_set_ensemble(sc_engine *eng, int n, long long ntraj_norm, const double *zi_dev,
+                           const double *probi_dev, void *stream);
+int sc_engine_set_ensemble_host(sc_engine *eng, int n, long long ntraj_norm, const double *zi_host,
+                                const double *probi_host, void *stream);
+
+/* step(potential, dt) x nsteps fused with autocorrelation()/ic_correlation() of every new time
+ * (propagators.py:645-655, 784-911; WM :1195-1389, 1577-1719).  For each of the nsteps new times writes
+ *   corr_host[5*k + 0..1] = sum_n C_auto^(qp) / (N probi (2 pi)^d)      (no e^{i t E0} phase)
+ *   corr_host[5*k + 2..3] = sum_n k_ic^(qp)   / (N probi (2 pi)^d) / hbar^2  (no phase)
+ *   corr_host[5*k + 4]    = mean over the local ensemble of (T+V) at the 4th RK4 stage (propagators.py:380)
+ * corr may be NULL.  The call synchronises the stream only when corr_host is given. */
+int sc_engine_step(sc_engine *eng, const sc_potential *pot, double dt, int nsteps, double *corr_host,
+                   void *stream);
+/* same, results left on the device (nsteps x 5 doubles), no synchronisation */
+int sc_engine_step_dev(sc_engine *eng, const sc_potential *pot, double dt, int nsteps, double *corr_dev,
+                       void *stream);
+
+/* autocorrelation() / ic_correlation(potential) at the CURRENT time without stepping; out_host[0..3] as above */
+int sc_engine_correlations(sc_engine *eng, const sc_potential *pot, double *out_host, void *stream);
+
+/* generic-potential stage interface (any Python object implementing the potential protocol):
+ * one RK4 step = 4 x { sc_engine_stage_positions -> user evaluates V, grad, hess -> sc_engine_stage_apply },
+ * then sc_engine_stage_finish (prefactor + branch tracking).  Arrays are batch-last device arrays. */
+int sc_engine_stage_positions(sc_engine *eng, int stage, double dt, double *q_dev, void *stream);
+int sc_engine_stage_apply(sc_engine *eng, int stage, double dt, const double *masses_dev, const double *V_dev,
+                          const double *grad_dev, const double *hess_dev, double *energy_sum_dev, void *stream);
+int sc_engine_stage_finish(sc_engine *eng, double dt, void *stream);
+/* correlations with caller-supplied NAC data: n1 = -tau1/m as constant vector (d) on the host */
+int sc_engine_correlations_n1(sc_engine *eng, const double *n1_host, double *out_host, void *stream);
+
+/* accessors (propagators.py:914-948): state in the reference's layout, prefactor and branch signs */
+int sc_engine_get_state(sc_engine *eng, double *y_dev, void *stream);            /* (2d+4d^2+1, n) */
+int sc_engine_set_state(sc_engine *eng, const double *y_dev, void *stream);
+int sc_engine_get_prefactor(sc_engine *eng, double *c_dev /* c128 (n) sqrt(det), principal branch */,
+                            double *c2_dev /* c128 (n) det */, double *signs_dev /* (3, n): C, detA, detM */,
+                            void *stream);
+int sc_engine_num_trajectories(const sc_engine *eng);
+/* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
+long long sc_engine_launch_count(const sc_engine *eng);
+/* name of the fused kernel variant the last sc_engine_step dispatched to (diagnostics) */
+const char *sc_engine_kernel_name(const sc_engine *eng);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMICLASSICAL_B200_H */

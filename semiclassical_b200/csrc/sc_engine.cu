@@ -1,0 +1,619 @@
+// sc_engine.cu -- C ABI (include/semiclassical_b200.h) and host-side dispatch of the sm_100a kernels.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/semiclassical_b200.h"
+#include "sc_kernels.cuh"
+#include "sc_mma.cuh"
+#include "sc_potentials.cuh"
+#include "sc_wm.cuh"
+
+using namespace sc;
+
+// ------------------------------------------------------------------ error handling ----------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) return fail(SC_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+extern "C" int sc_abi_version(void) { return SC_ABI_VERSION; }
+extern "C" const char *sc_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ device buffers ----------
+struct DevPool {
+  std::vector<void *> ptrs;
+  ~DevPool() { for (void *p : ptrs) cudaFree(p); }
+  cudaError_t upload(const double *host, size_t n, const double **out) {
+    double *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(double) * (n ? n : 1));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    if (n) e = cudaMemcpy(p, host, sizeof(double) * n, cudaMemcpyHostToDevice);
+    *out = p;
+    return e;
+  }
+  template <typename T>
+  cudaError_t alloc(size_t n, T **out) {
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sizeof(T) * (n ? n : 1));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(p);
+    *out = reinterpret_cast<T *>(p);
+    return e;
+  }
+};
+
+struct sc_potential {
+  PotDev dev;
+  DevPool pool;
+  std::vector<double> imass, n1;  // host copies for the IC constants
+};
+
+struct sc_engine {
+  sc_engine_config cfg;
+  EngDev dev;
+  DevPool pool;       // constants
+  DevPool ens;        // ensemble-sized buffers
+  std::vector<double> hR, hG0iG, hp0;  // host: R = G0 iGi0 Gi, G0 iGi0, p0
+  const double *oiA = nullptr, *oiB = nullptr, *oiC = nullptr;
+  double *d_wR = nullptr, *d_wG = nullptr;
+  const sc_potential *nac_pot = nullptr;
+  std::vector<double> nac_cache;
+  double *partials = nullptr;
+  size_t partials_cap = 0;
+  double *corr_dev = nullptr;
+  size_t corr_cap = 0;
+  long long ntraj_norm = 0;
+  long long launches = 0;
+  int sm_count = 148;
+  const char *kernel_name = "none";
+  WMState wm;
+  // generic-potential stage path
+  double *stage_buf = nullptr;
+};
+
+// ------------------------------------------------------------------ potentials --------------
+static int pot_common(sc_potential *p, int type, int d, const double *masses, const double *nac) {
+  p->dev = PotDev();
+  p->dev.type = type;
+  p->dev.d = d;
+  p->imass.resize(d);
+  p->n1.resize(d);
+  for (int i = 0; i < d; ++i) {
+    p->imass[i] = 1.0 / (masses ? masses[i] : 1.0);
+    p->n1[i] = -(nac ? nac[i] : 1.0) * p->imass[i];
+  }
+  CU(p->pool.upload(p->imass.data(), d, &p->dev.imass));
+  CU(p->pool.upload(p->n1.data(), d, &p->dev.n1));
+  return SC_OK;
+}
+
+static int check_dim(int d) {
+  if (d < 1 || d > SC_MAX_DIM) return fail(SC_ERR_UNSUPPORTED, "dimension %d outside [1, %d]", d, SC_MAX_DIM);
+  return SC_OK;
+}
+
+extern "C" int sc_potential_create_morse(sc_potential **out, int d, const double *omega, const double *a,
+                                         const double *D, int all_harmonic, const double *nac) {
+  if (!out || !omega || !a || !D || !nac) return fail(SC_ERR_INVALID, "null argument");
+  if (int rc = check_dim(d)) return rc;
+  sc_potential *p = new sc_potential();
+  int rc = pot_common(p, POT_MORSE, d, nullptr, nac);
+  if (rc) { delete p; return rc; }
+  CU(p->pool.upload(omega, d, &p->dev.omega));
+  CU(p->pool.upload(a, d, &p->dev.a));
+  CU(p->pool.upload(D, d, &p->dev.D));
+  p->dev.all_harmonic = all_harmonic;
+  *out = p;
+  return SC_OK;
+}
+
+extern "C" int sc_potential_create_rotated_morse(sc_potential **out, int d, const double *omega, const double *a,
+                                                 const double *D, int all_harmonic, const double *nac,
+                                                 const double *Q) {
+  if (!Q) return fail(SC_ERR_INVALID, "null argument");
+  int rc = sc_potential_create_morse(out, d, omega, a, D, all_harmonic, nac);
+  if (rc) return rc;
+  (*out)->dev.type = POT_ROTATED_MORSE;
+  CU((*out)->pool.upload(Q, (size_t)d * d, &(*out)->dev.Q));
+  return SC_OK;
+}
+
+extern "C" int sc_potential_create_nonharmonic(sc_potential **out, int d, const double *eps, const double *b) {
+  if (!out || !eps || !b) return fail(SC_ERR_INVALID, "null argument");
+  if (int rc = check_dim(d)) return rc;
+  sc_potential *p = new sc_potential();
+  int rc = pot_common(p, POT_NONHARMONIC, d, nullptr, nullptr);  // masses 1, tau1 = 1
+  if (rc) { delete p; return rc; }
+  CU(p->pool.upload(eps, d, &p->dev.eps));
+  CU(p->pool.upload(b, d, &p->dev.b));
+  *out = p;
+  return SC_OK;
+}
+
+extern "C" int sc_potential_create_harmonic(sc_potential **out, int d, const double *pos0, double energy0,
+                                            const double *grad0, const double *hess0, const double *masses,
+                                            const double *nac) {
+  if (!out || !pos0 || !grad0 || !hess0 || !masses || !nac) return fail(SC_ERR_INVALID, "null argument");
+  if (int rc = check_dim(d)) return rc;
+  sc_potential *p = new sc_potential();
+  int rc = pot_common(p, POT_HARMONIC, d, masses, nac);
+  if (rc) { delete p; return rc; }
+  CU(p->pool.upload(pos0, d, &p->dev.pos0));
+  CU(p->pool.upload(grad0, d, &p->dev.grad0));
+  CU(p->pool.upload(hess0, (size_t)d * d, &p->dev.hess0));
+  p->dev.e0 = energy0;
+  *out = p;
+  return SC_OK;
+}
+
+extern "C" int sc_potential_create_gdml(sc_potential **out, int n_atoms, int n_train, int n_desc,
+                                        const double *xs_train, const double *jx_alphas, double sig, double c,
+                                        double std, const double *masses, const double *nac) {
+  if (!out || !xs_train || !jx_alphas || !masses || !nac) return fail(SC_ERR_INVALID, "null argument");
+  const int d = 3 * n_atoms;
+  if (int rc = check_dim(d)) return rc;
+  if (n_desc != n_atoms * (n_atoms - 1) / 2) return fail(SC_ERR_INVALID, "n_desc != N(N-1)/2");
+  sc_potential *p = new sc_potential();
+  int rc = pot_common(p, POT_GDML, d, masses, nac);
+  if (rc) { delete p; return rc; }
+  CU(p->pool.upload(xs_train, (size_t)n_train * n_desc, &p->dev.xs_train));
+  CU(p->pool.upload(jx_alphas, (size_t)n_train * n_desc, &p->dev.jx_alphas));
+  p->dev.n_atoms = n_atoms;
+  p->dev.n_train = n_train;
+  p->dev.n_desc = n_desc;
+  p->dev.sig = sig;
+  p->dev.e0 = c;
+  p->dev.gstd = std;
+  *out = p;
+  return SC_OK;
+}
+
+extern "C" int sc_potential_set_origin(sc_potential *pot, double origin) {
+  if (!pot) return fail(SC_ERR_INVALID, "null potential");
+  pot->dev.origin = origin;
+  return SC_OK;
+}
+extern "C" int sc_potential_dimensions(const sc_potential *pot) { return pot ? pot->dev.d : -1; }
+extern "C" int sc_potential_destroy(sc_potential *pot) {
+  delete pot;
+  return SC_OK;
+}
+
+extern "C" int sc_potential_eval(const sc_potential *pot, int n, const double *r, double *V, double *grad,
+                                 double *hess, void *stream) {
+  if (!pot || !r || !V) return fail(SC_ERR_INVALID, "null argument");
+  if (n <= 0) return SC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = launch_potential_eval(pot->dev, n, r, V, grad, hess, st);
+  if (rc) return fail(SC_ERR_UNSUPPORTED, "potential type %d not supported by sc_potential_eval", pot->dev.type);
+  CU(cudaGetLastError());
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ engine ------------------
+static bool is_diagonal(const double *A, int d) {
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j)
+      if (i != j && A[i * d + j] != 0.0) return false;
+  return true;
+}
+
+extern "C" int sc_engine_create(sc_engine **out, const sc_engine_config *cfg) {
+  if (!out || !cfg) return fail(SC_ERR_INVALID, "null argument");
+  const int d = cfg->d, dr = cfg->dr;
+  if (int rc = check_dim(d)) return rc;
+  if (dr < 1 || dr > d) return fail(SC_ERR_INVALID, "rank %d outside [1, %d]", dr, d);
+  sc_engine *e = new sc_engine();
+  e->cfg = *cfg;
+  EngDev &D = e->dev;
+  D = EngDev();
+  D.d = d;
+  D.dr = dr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  // diagonal fast path: all three width matrices diagonal and of full rank (AS models: Gamma = diag(omega))
+  const bool diag = dr == d && is_diagonal(cfg->Gamma_0, d) && is_diagonal(cfg->Gamma_i, d) && is_diagonal(cfg->Gamma_t, d);
+  D.diag = diag ? 1 : 0;
+  const size_t dd = (size_t)d * d;
+#define UP(ptr, src, n)                                             \
+  do {                                                              \
+    cudaError_t ce = e->pool.upload(src, n, &ptr);                  \
+    if (ce != cudaSuccess) { delete e; return fail(SC_ERR_CUDA, "upload failed: %s", cudaGetErrorString(ce)); } \
+  } while (0)
+  UP(D.L1, cfg->L1, (size_t)dr * d);
+  UP(D.L2, cfg->L2, (size_t)dr * d);
+  UP(D.R1, cfg->R1, (size_t)d * dr);
+  UP(D.R2, cfg->R2, (size_t)d * dr);
+  UP(D.q0, cfg->q0, d);
+  UP(D.p0, cfg->p0, d);
+  if (diag) {
+    std::vector<double> sgt(d), isgt(d), sgi(d), isgi(d), a(d), b(d), c(d);
+    for (int i = 0; i < d; ++i) {
+      sgt[i] = std::sqrt(cfg->Gamma_t[i * d + i]);
+      isgt[i] = 1.0 / sgt[i];
+      sgi[i] = std::sqrt(cfg->Gamma_i[i * d + i]);
+      isgi[i] = 1.0 / sgi[i];
+    }
+    UP(D.sgt, sgt.data(), d); UP(D.isgt, isgt.data(), d); UP(D.sgi, sgi.data(), d); UP(D.isgi, isgi.data(), d);
+    for (int i = 0; i < d; ++i) { a[i] = cfg->ot0_A[i * d + i]; b[i] = cfg->ot0_B[i * d + i]; c[i] = cfg->ot0_C[i * d + i]; }
+    UP(D.otA, a.data(), d); UP(D.otB, b.data(), d); UP(D.otC, c.data(), d);
+    for (int i = 0; i < d; ++i) { a[i] = cfg->oi0_A[i * d + i]; b[i] = cfg->oi0_B[i * d + i]; c[i] = cfg->oi0_C[i * d + i]; }
+    UP(e->oiA, a.data(), d); UP(e->oiB, b.data(), d); UP(e->oiC, c.data(), d);
+  } else {
+    UP(D.otA, cfg->ot0_A, dd); UP(D.otB, cfg->ot0_B, dd); UP(D.otC, cfg->ot0_C, dd);
+    UP(e->oiA, cfg->oi0_A, dd); UP(e->oiB, cfg->oi0_B, dd); UP(e->oiC, cfg->oi0_C, dd);
+  }
+  D.ot_fac = cfg->ot0_fac;
+  // host copies for the NAC-dependent vectors wR = R n1, wG = (G0 iGi0)^T n1  (propagators.py:894-903)
+  e->hG0iG.assign(dd, 0.0);
+  e->hR.assign(dd, 0.0);
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += cfg->Gamma_0[i * d + k] * cfg->iGi0[k * d + j];
+      e->hG0iG[i * d + j] = s;
+    }
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += e->hG0iG[i * d + k] * cfg->Gamma_i[k * d + j];
+      e->hR[i * d + j] = s;
+    }
+  e->hp0.assign(cfg->p0, cfg->p0 + d);
+  {
+    cudaError_t ce = e->pool.alloc((size_t)d, &e->d_wR);
+    if (ce == cudaSuccess) ce = e->pool.alloc((size_t)d, &e->d_wG);
+    if (ce != cudaSuccess) { delete e; return fail(SC_ERR_CUDA, "alloc failed: %s", cudaGetErrorString(ce)); }
+  }
+  D.wR = e->d_wR;
+  D.wG = e->d_wG;
+  if (cfg->wm) {
+    int rc = wm_setup(e->wm, *cfg, e->pool);
+    if (rc) { delete e; return fail(SC_ERR_CUDA, "WM constant upload failed"); }
+  }
+#undef UP
+  // the config's pointers are the caller's; never dereference them after create
+  e->cfg.L1 = e->cfg.L2 = e->cfg.R1 = e->cfg.R2 = e->cfg.U = e->cfg.q0 = e->cfg.p0 = nullptr;
+  e->cfg.oi0_A = e->cfg.oi0_B = e->cfg.oi0_C = e->cfg.ot0_A = e->cfg.ot0_B = e->cfg.ot0_C = nullptr;
+  e->cfg.Gamma_0 = e->cfg.Gamma_i = e->cfg.Gamma_t = e->cfg.iGi0 = e->cfg.iGamma_0 = nullptr;
+  *out = e;
+  return SC_OK;
+}
+
+extern "C" int sc_engine_destroy(sc_engine *e) {
+  delete e;
+  return SC_OK;
+}
+
+extern "C" int sc_engine_num_trajectories(const sc_engine *e) { return e ? e->dev.n : -1; }
+extern "C" long long sc_engine_launch_count(const sc_engine *e) { return e ? e->launches : -1; }
+extern "C" const char *sc_engine_kernel_name(const sc_engine *e) { return e ? e->kernel_name : ""; }
+
+// NAC-dependent constants for the potential in use
+static int set_nac(sc_engine *e, const double *n1, cudaStream_t st) {
+  const int d = e->dev.d;
+  if ((int)e->nac_cache.size() == d && std::memcmp(e->nac_cache.data(), n1, sizeof(double) * d) == 0) return SC_OK;
+  std::vector<double> w(2 * d, 0.0);
+  double p0n1 = 0.0;
+  for (int i = 0; i < d; ++i) {
+    double s = 0.0, g = 0.0;
+    for (int j = 0; j < d; ++j) { s += e->hR[i * d + j] * n1[j]; g += e->hG0iG[j * d + i] * n1[j]; }
+    w[i] = s;
+    w[d + i] = g;
+    p0n1 += e->hp0[i] * n1[i];
+  }
+  // synchronous copies: the previous values may still be in use by kernels in flight on `st`
+  CU(cudaStreamSynchronize(st));
+  CU(cudaMemcpy(e->d_wR, w.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->d_wG, w.data() + d, sizeof(double) * d, cudaMemcpyHostToDevice));
+  e->dev.p0n1 = p0n1;
+  e->nac_cache.assign(n1, n1 + d);
+  if (e->cfg.wm) wm_set_nac(e->wm, n1, d);
+  return SC_OK;
+}
+
+struct LaunchPlan {
+  int tpt, ept, groups_per_cta, threads, grid;
+  size_t smem;
+  SmemLayout L;
+  bool mma;
+};
+
+static int plan_launch(const sc_engine *e, int mode, bool allow_mma, LaunchPlan &pl) {
+  const int d = e->dev.d, dr = e->dev.dr, n = e->dev.n;
+  const int ne = 2 * d * d;
+  pl.mma = false;
+  int ldu = 2 * d, ldh = d;
+  if (d <= 16) {
+    pl.tpt = 32; pl.groups_per_cta = 4; pl.threads = 128;
+    pl.ept = (ne + 31) / 32;
+  } else {
+    pl.tpt = (d <= 45) ? 256 : 320;
+    pl.groups_per_cta = 1; pl.threads = pl.tpt;
+    pl.ept = (ne + pl.tpt - 1) / pl.tpt;
+    if (allow_mma && mode == MODE_STEP && mma_supported(d)) {
+      pl.mma = true;
+      mma_leading_dims(d, ldu, ldh);
+      pl.tpt = pl.threads = mma_threads(d);
+    }
+  }
+  pl.L = make_layout(d, dr, ldu, ldh);
+  pl.smem = sizeof(double) * (size_t)pl.L.total * pl.groups_per_cta;
+  if (pl.smem > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "shared-memory footprint %zu B exceeds 227 KB (d = %d)", pl.smem, d);
+  const int groups_needed = n;
+  int ctas_per_sm = (int)((227 * 1024) / (pl.smem + 1024));
+  const int max_by_threads = 2048 / pl.threads;
+  if (ctas_per_sm > max_by_threads) ctas_per_sm = max_by_threads;
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  if (ctas_per_sm > 8) ctas_per_sm = 8;
+  int grid = e->sm_count * ctas_per_sm;
+  const int need = (groups_needed + pl.groups_per_cta - 1) / pl.groups_per_cta;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  pl.grid = grid;
+  return SC_OK;
+}
+
+template <int TPT, int EPT>
+static cudaError_t launch_generic(const LaunchPlan &pl, const EngDev &E, const PotDev &P, double h, int nsteps, int mode,
+                                  double *partials, cudaStream_t st) {
+  auto kern = k_hk_generic<TPT, EPT>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+  if (ce != cudaSuccess) return ce;
+  kern<<<pl.grid, pl.threads, pl.smem, st>>>(E, P, h, nsteps, mode, partials, pl.L);
+  return cudaGetLastError();
+}
+
+static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, int mode, double *out_dev, cudaStream_t st,
+                         bool allow_mma = true) {
+  LaunchPlan pl;
+  if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
+  const int nrows = (mode == MODE_STEP) ? nsteps : 1;
+  const int ngroups = pl.grid * pl.groups_per_cta;
+  const size_t need = (size_t)ngroups * nrows * 5;
+  if (need > e->partials_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->partials) cudaFree(e->partials);
+    e->partials = nullptr;
+    CU(cudaMalloc(&e->partials, sizeof(double) * need));
+    e->partials_cap = need;
+  }
+  if (mode != MODE_INIT) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
+  cudaError_t ce = cudaSuccess;
+  if (pl.mma) {
+    ce = launch_mma(pl.grid, pl.threads, pl.smem, e->dev, P, h, nsteps, e->partials, pl.L, st);
+    e->kernel_name = "k_hk_mma";
+  } else {
+    e->kernel_name = "k_hk_generic";
+#define CASE(T, E_) ce = launch_generic<T, E_>(pl, e->dev, P, h, nsteps, mode, e->partials, st)
+    if (pl.tpt == 32) {
+      if (pl.ept <= 2) CASE(32, 2);
+      else if (pl.ept <= 4) CASE(32, 4);
+      else if (pl.ept <= 9) CASE(32, 9);
+      else CASE(32, 16);
+    } else if (pl.tpt == 256) {
+      if (pl.ept <= 8) CASE(256, 8);
+      else CASE(256, 16);
+    } else {
+      CASE(320, 26);
+    }
+#undef CASE
+  }
+  if (ce != cudaSuccess) return fail(SC_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(ce));
+  e->launches += 1;
+  if (mode != MODE_INIT) {
+    k_reduce_partials<<<nrows, 160, 0, st>>>(e->partials, ngroups, nrows, 1.0 / (double)e->ntraj_norm,
+                                             1.0 / (double)e->dev.n, out_dev);
+    CU(cudaGetLastError());
+    e->launches += 1;
+  }
+  return SC_OK;
+}
+
+static int ensure_corr(sc_engine *e, int nsteps, cudaStream_t st) {
+  const size_t need = (size_t)nsteps * 5;
+  if (need > e->corr_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->corr_dev) cudaFree(e->corr_dev);
+    e->corr_dev = nullptr;
+    CU(cudaMalloc(&e->corr_dev, sizeof(double) * need));
+    e->corr_cap = need;
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm, const double *zi, const double *probi,
+                                      void *stream) {
+  if (!e || !zi || !probi) return fail(SC_ERR_INVALID, "null argument");
+  if (n < 1) return fail(SC_ERR_INVALID, "need at least one trajectory");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  EngDev &D = e->dev;
+  const int d = D.d;
+  CU(cudaStreamSynchronize(st));
+  e->ens = DevPool();  // releases the previous ensemble
+  D.n = n;
+  D.qps = (2 * d + 1 + 1) & ~1;
+  D.rs = D.qps + 4 * d * d;
+  e->ntraj_norm = ntraj_norm > 0 ? ntraj_norm : n;
+  double *zt = nullptr;
+  double2 *wvi = nullptr;
+  CU(e->ens.alloc((size_t)n * D.rs, &D.rec));
+  CU(e->ens.alloc((size_t)n * 2 * d, &zt));
+  CU(e->ens.alloc((size_t)n, &wvi));
+  CU(e->ens.alloc((size_t)n, &D.c2));
+  CU(e->ens.alloc((size_t)n, &D.c));
+  CU(e->ens.alloc((size_t)n, &D.sign));
+  D.zt = zt;
+  D.wvi = wvi;
+  CU(cudaMemsetAsync(D.c2, 0, sizeof(double2) * n, st));
+  CU(cudaMemsetAsync(D.c, 0, sizeof(double2) * n, st));
+  CU(cudaMemsetAsync(D.sign, 0, sizeof(double) * n, st));
+  const double inv2pid = std::pow(2.0 * M_PI, -(double)d);
+  k_init_records<<<(n + 127) / 128, 128, 0, st>>>(D, zi, probi, e->oiA, e->oiB, e->oiC, e->cfg.oi0_fac, inv2pid, zt, wvi);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  // prefactor at t = 0 initialises the branch trackers (propagators.py:628-631)
+  PotDev none = PotDev();
+  none.d = d;
+  none.imass = D.q0;  // never dereferenced beyond d entries in MODE_INIT
+  if (int rc = run_hk_kernel(e, none, 0.0, 0, MODE_INIT, nullptr, st)) return rc;
+  if (e->cfg.wm) {
+    if (int rc = wm_alloc(e->wm, e->ens, D, st)) return fail(SC_ERR_CUDA, "WM allocation failed");
+    if (int rc = wm_prefactor_launch(e->wm, D, /*init=*/1, st)) return fail(SC_ERR_CUDA, "WM prefactor launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    e->launches += 1;
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_engine_set_ensemble_host(sc_engine *e, int n, long long ntraj_norm, const double *zi_host,
+                                           const double *probi_host, void *stream) {
+  if (!e || !zi_host || !probi_host) return fail(SC_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *zi = nullptr, *pr = nullptr;
+  const size_t nz = (size_t)2 * e->dev.d * n;
+  CU(cudaMalloc(&zi, sizeof(double) * nz));
+  CU(cudaMalloc(&pr, sizeof(double) * n));
+  CU(cudaMemcpyAsync(zi, zi_host, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(pr, probi_host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  int rc = sc_engine_set_ensemble(e, n, ntraj_norm, zi, pr, stream);
+  cudaStreamSynchronize(st);
+  cudaFree(zi);
+  cudaFree(pr);
+  return rc;
+}
+
+static int check_step_args(sc_engine *e, const sc_potential *pot) {
+  if (!e || !pot) return fail(SC_ERR_INVALID, "null argument");
+  if (e->dev.n < 1) return fail(SC_ERR_INVALID, "initial_conditions / sc_engine_set_ensemble has not been called");
+  if (pot->dev.d != e->dev.d) return fail(SC_ERR_INVALID, "potential has wrong dimensions");
+  return SC_OK;
+}
+
+extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double dt, int nsteps, double *corr_dev,
+                                  void *stream) {
+  if (int rc = check_step_args(e, pot)) return rc;
+  if (nsteps < 1) return SC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = set_nac(e, pot->n1.data(), st)) return rc;
+  if (pot->dev.type == POT_GDML) return fail(SC_ERR_UNSUPPORTED, "sGDML potentials run through the stage interface");
+  if (!corr_dev) {
+    if (int rc = ensure_corr(e, nsteps, st)) return rc;
+    corr_dev = e->corr_dev;
+  }
+  if (!e->cfg.wm) return run_hk_kernel(e, pot->dev, dt, nsteps, MODE_STEP, corr_dev, st);
+  // Walton-Manolopoulos: the HK kernel advances the trajectories one step at a time, the WM kernel evaluates
+  // the Filinov-smoothed prefactor pieces and the WM contributions of every new time
+  for (int k = 0; k < nsteps; ++k) {
+    if (int rc = ensure_corr(e, 1, st)) return rc;
+    if (int rc = run_hk_kernel(e, pot->dev, dt, 1, MODE_STEP, e->wm.scratch5, st)) return rc;
+    if (wm_prefactor_launch(e->wm, e->dev, 0, st)) return fail(SC_ERR_CUDA, "WM prefactor launch failed");
+    if (wm_corr_launch(e->wm, e->dev, pot->dev, 1.0 / (double)e->ntraj_norm, corr_dev + 5 * k, e->wm.scratch5, st))
+      return fail(SC_ERR_CUDA, "WM correlation launch failed");
+    e->launches += 2;
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_engine_step(sc_engine *e, const sc_potential *pot, double dt, int nsteps, double *corr_host,
+                              void *stream) {
+  if (int rc = check_step_args(e, pot)) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (int rc = ensure_corr(e, nsteps, st)) return rc;
+  if (int rc = sc_engine_step_dev(e, pot, dt, nsteps, e->corr_dev, stream)) return rc;
+  if (corr_host) {
+    CU(cudaMemcpyAsync(corr_host, e->corr_dev, sizeof(double) * 5 * nsteps, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return SC_OK;
+}
+
+static int correlations_impl(sc_engine *e, const PotDev &P, const double *n1, double *out_host, cudaStream_t st) {
+  if (int rc = set_nac(e, n1, st)) return rc;
+  if (int rc = ensure_corr(e, 1, st)) return rc;
+  if (!e->cfg.wm) {
+    if (int rc = run_hk_kernel(e, P, 0.0, 1, MODE_CORR, e->corr_dev, st)) return rc;
+  } else {
+    if (wm_corr_launch(e->wm, e->dev, P, 1.0 / (double)e->ntraj_norm, e->corr_dev, nullptr, st))
+      return fail(SC_ERR_CUDA, "WM correlation launch failed");
+    e->launches += 1;
+  }
+  CU(cudaMemcpyAsync(out_host, e->corr_dev, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return SC_OK;
+}
+
+extern "C" int sc_engine_correlations(sc_engine *e, const sc_potential *pot, double *out_host, void *stream) {
+  if (int rc = check_step_args(e, pot)) return rc;
+  if (!out_host) return fail(SC_ERR_INVALID, "null argument");
+  return correlations_impl(e, pot->dev, pot->n1.data(), out_host, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sc_engine_correlations_n1(sc_engine *e, const double *n1_host, double *out_host, void *stream) {
+  if (!e || !n1_host || !out_host) return fail(SC_ERR_INVALID, "null argument");
+  if (e->dev.n < 1) return fail(SC_ERR_INVALID, "no ensemble");
+  PotDev none = PotDev();
+  none.d = e->dev.d;
+  none.imass = e->dev.q0;
+  none.n1 = nullptr;
+  // the WM kernel reads n1 from device memory: stage it through the engine's cache
+  return correlations_impl(e, none, n1_host, out_host, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sc_engine_get_state(sc_engine *e, double *y, void *stream) {
+  if (!e || !y || e->dev.n < 1) return fail(SC_ERR_INVALID, "no ensemble / null argument");
+  k_export_state<<<e->sm_count * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(e->dev, y, 1);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return SC_OK;
+}
+
+extern "C" int sc_engine_set_state(sc_engine *e, const double *y, void *stream) {
+  if (!e || !y || e->dev.n < 1) return fail(SC_ERR_INVALID, "no ensemble / null argument");
+  k_export_state<<<e->sm_count * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(e->dev, const_cast<double *>(y), 0);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return SC_OK;
+}
+
+extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, double *signs, void *stream) {
+  if (!e || e->dev.n < 1) return fail(SC_ERR_INVALID, "no ensemble");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n;
+  if (c) CU(cudaMemcpyAsync(c, e->dev.c, sizeof(double2) * n, cudaMemcpyDeviceToDevice, st));
+  if (c2) CU(cudaMemcpyAsync(c2, e->dev.c2, sizeof(double2) * n, cudaMemcpyDeviceToDevice, st));
+  if (signs) {
+    CU(cudaMemcpyAsync(signs, e->dev.sign, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (e->cfg.wm) {
+      CU(cudaMemcpyAsync(signs + n, e->wm.signA, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(signs + 2 * n, e->wm.signM, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    } else {
+      std::vector<double> ones(2 * (size_t)n, 1.0);
+      CU(cudaMemcpyAsync(signs + n, ones.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
+      CU(cudaStreamSynchronize(st));
+    }
+  }
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ generic-potential stage path
+#include "sc_stage.cuh"

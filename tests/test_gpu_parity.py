@@ -1,0 +1,130 @@
+"""
+GPU parity tests (run with -m gpu on the B200): the CUDA path, called through the C ABI via the Python mirror of
+the reference interface, against (a) the golden vectors of the unmodified reference and (b) the C oracle on
+seeded inputs.  Tolerance: max_t |C - C_ref| / max_t |C_ref| <= 1e-9 (BASELINE.json north_star), identical
+sqrt-branch sign vectors.
+"""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import T, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.0e-9
+HK_GOLDENS = ["hk_as5_chi002", "hk_as5_chi000", "hk_1d", "hk_as5_rot", "hk_methylium", "hk_as24_rot", "hk_as60",
+              "hk_as60_rot"]
+
+
+def run_loop(pr, pot, dt, nt, e0):
+    """the reference's driver loop (cli.py:401-436)"""
+    auto, ic = np.zeros(nt, complex), np.zeros(nt, complex)
+    for k in range(nt):
+        auto[k] = pr.autocorrelation(e0)
+        ic[k] = pr.ic_correlation(pot, e0)
+        pr.step(pot, dt)
+    return auto, ic
+
+
+@pytest.mark.parametrize("name", HK_GOLDENS)
+def test_hk_step_loop_matches_reference(name, cuda_device):
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    auto, ic = run_loop(pr, pot, float(g['dt']), int(g['nt']), float(g['energy0_es']))
+    assert relerr(auto, g['autocorrelation']) < TOL
+    assert relerr(ic, g['ic_correlation']) < TOL
+    nk = g['y_final'].shape[1]
+    assert relerr(pr.y[:, :nk].cpu().numpy(), g['y_final']) < TOL
+    assert relerr(pr.c.cpu().numpy(), g['c_final']) < TOL
+    signs = pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy()
+    assert np.array_equal(signs, g['signs_C'])
+    assert abs(float(pr.t) - float(g['t_final'])) < 1e-12 * max(1.0, abs(float(g['t_final'])))
+
+
+@pytest.mark.parametrize("name", HK_GOLDENS)
+def test_hk_fused_propagate_matches_reference(name, cuda_device):
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    nt, e0 = int(g['nt']), float(g['energy0_es'])
+    a0, i0 = pr.autocorrelation(e0), pr.ic_correlation(pot, e0)
+    a, i = pr.propagate(pot, float(g['dt']), nt - 1, e0)
+    assert relerr(np.concatenate(([a0], a)), g['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), g['ic_correlation']) < TOL
+
+
+def test_initial_autocorrelation_is_one(cuda_device):
+    g = helpers.load_golden("hk_as5_chi002")
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    assert abs(pr.autocorrelation(float(g['energy0_es'])) - 1.0) < 1e-12
+
+
+def test_shards_sum_to_whole(cuda_device):
+    """multi-GPU decomposition on one device: sum over shards == unsharded"""
+    g = helpers.load_golden("hk_as5_rot")
+    pot = helpers.potential_from_golden(g)
+    n, nt, e0, dt = len(g['probi']), 30, float(g['energy0_es']), float(g['dt'])
+    acc_a, acc_i = np.zeros(nt, complex), np.zeros(nt, complex)
+    for sl in (slice(0, 137), slice(137, 300), slice(300, n)):
+        pr = helpers.propagator_from_golden(g, cuda_device, nslice=sl)
+        a, i = pr.propagate(pot, dt, nt, e0)
+        acc_a += a
+        acc_i += i
+    assert relerr(acc_a, g['autocorrelation'][1:nt + 1]) < TOL
+    assert relerr(acc_i, g['ic_correlation'][1:nt + 1]) < TOL
+
+
+def test_engine_against_oracle_on_fresh_ensemble(cuda_device):
+    """seeded ensemble that is in no fixture: CUDA path vs the C oracle, 5-mode AS, 4096 trajectories"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_5modes(0.02)
+    G = np.diag(m.omega)
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, 4096, np.random.default_rng(42))
+    dt, nt = workloads.test_time_grid()
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi, probi,
+                     dt, nt, m.en_zpt)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    auto, ic = run_loop(pr, pot, dt, nt, m.en_zpt)
+    assert relerr(auto, ref['autocorrelation']) < TOL
+    assert relerr(ic, ref['ic_correlation']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
+
+
+@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_1d", "hk_methylium", "hk_as5_rot"])
+def test_potential_kernels_against_oracle(name, cuda_device):
+    """batched harmonic_approximation kernels vs the oracle's potentials"""
+    from oracle import oracle
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    opot, _, _ = oracle.from_golden(g)
+    d = pot.dimensions()
+    r = g['zi'][:d, :257].copy()
+    V, grad, hess = pot.harmonic_approximation(T(r).to(cuda_device))
+    Vo, go, ho = opot.eval(r)
+    assert np.abs(V.cpu().numpy() - Vo).max() <= 1e-12 * max(1.0, np.abs(Vo).max())
+    assert relerr(grad.cpu().numpy(), go) < 1e-12
+    assert relerr(hess.cpu().numpy(), ho) < 1e-12
+
+
+def test_energy_guard_raises(cuda_device):
+    """a time step far too large violates energy conservation -> RuntimeError (propagators.py:385-398)"""
+    g = helpers.load_golden("hk_1d")
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    with pytest.raises(RuntimeError, match="not conserved"):
+        for _ in range(50):
+            pr.step(pot, 3.0)
+
+
+def test_wrong_dimension_is_rejected(cuda_device):
+    g = helpers.load_golden("hk_1d")
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    pot5 = helpers.potential_from_golden(helpers.load_golden("hk_as5_chi002"))
+    with pytest.raises(AssertionError):
+        pr.step(pot5, 0.1)
