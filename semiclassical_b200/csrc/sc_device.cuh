@@ -280,6 +280,79 @@ __device__ __forceinline__ double2 lu_det(double2 *Cm, int dr, int *ibuf, double
   return det;
 }
 
+// CTA-wide variant (TPT a multiple of 32, dr <= 64): one barrier per column.
+//   rows -> warps (row i belongs to warp i % NW), columns -> lanes: no integer division, conflict-free row
+//   accesses; the pivot of column k+1 is found while column k is eliminated (each warp reduces its rows with
+//   redux.sync on a packed (magnitude, row) key, the NW partial keys are combined by every warp after the
+//   barrier); retired rows are tracked in a 64-bit register mask, the permutation parity with popcounts.
+// wkey: 2 x 32 unsigned of shared scratch (double-buffered partial keys). Result valid on every thread.
+__device__ __forceinline__ unsigned pivot_key(double2 v, int row) {
+  const double m = v.x * v.x + v.y * v.y;
+  return (static_cast<unsigned>(__double2hiint(m)) & ~63u) | static_cast<unsigned>(row);
+}
+
+template <int TPT>
+__device__ __forceinline__ double2 lu_det_cta(double2 *Cm, int dr, unsigned *wkey, int t) {
+  constexpr int NW = TPT / 32;
+  constexpr int MAXR = (64 + NW - 1) / NW;   // rows per warp
+  const int lane = t & 31, warp = t >> 5;
+  unsigned long long done = 0ull;
+  double2 det = make_double2(1.0, 0.0);
+  int inversions = 0;
+  {
+    // partial keys of column 0
+    unsigned key = 0u;
+    const int i = warp + NW * lane;
+    if (lane < MAXR && i < dr) key = pivot_key(Cm[i * dr], i);
+    key = __reduce_max_sync(0xffffffffu, key);
+    if (lane == 0) wkey[warp] = key;
+  }
+  __syncthreads();
+  for (int k = 0; k < dr; ++k) {
+    const unsigned *wk = wkey + (k & 1) * 32;
+    unsigned kk = (lane < NW) ? wk[lane] : 0u;
+    kk = __reduce_max_sync(0xffffffffu, kk);
+    const int p = static_cast<int>(kk & 63u);
+    inversions += __popcll(done >> p);          // earlier pivots with a larger row index
+    done |= 1ull << p;
+    const double2 pv = Cm[p * dr + k];
+    det = cmul(det, pv);
+    if (k + 1 == dr) break;
+    const double rn = 1.0 / (pv.x * pv.x + pv.y * pv.y);
+    const double2 ip = make_double2(pv.x * rn, -pv.y * rn);
+    const int j0 = k + 1 + lane, j1 = j0 + 32;
+    double2 u0 = make_double2(0.0, 0.0), u1 = u0;
+    if (j0 < dr) u0 = Cm[p * dr + j0];
+    if (j1 < dr) u1 = Cm[p * dr + j1];
+    unsigned nkey = 0u;
+#pragma unroll
+    for (int m = 0; m < MAXR; ++m) {
+      const int i = warp + NW * m;
+      if (i < dr && !((done >> i) & 1ull)) {
+        double2 *row = Cm + i * dr;
+        const double2 f = cmul(row[k], ip);
+        if (j0 < dr) {
+          double2 v = row[j0];
+          v.x -= f.x * u0.x - f.y * u0.y;
+          v.y -= f.x * u0.y + f.y * u0.x;
+          row[j0] = v;
+          if (lane == 0) nkey = max(nkey, pivot_key(v, i));
+        }
+        if (j1 < dr) {
+          double2 v = row[j1];
+          v.x -= f.x * u1.x - f.y * u1.y;
+          v.y -= f.x * u1.y + f.y * u1.x;
+          row[j1] = v;
+        }
+      }
+    }
+    if (lane == 0) wkey[((k + 1) & 1) * 32 + warp] = nkey;
+    __syncthreads();
+  }
+  if (inversions & 1) { det.x = -det.x; det.y = -det.y; }
+  return det;
+}
+
 // ------------------------------------------------------------------ prefactor assembly -------
 // Cm (dr x dr complex) = 1/2 [ L1 Mqq R1 + L2 Mpp R2 - i L1 Mqp R2 + i L2 Mpq R1 ]     (propagators.py:969-994)
 // Ub = [Mqq|Mqp], Vb = [Mpq|Mpp] (d x 2d, ld = ldu) in shared memory; T: shared scratch d x dr.

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -387,6 +388,7 @@ static cudaError_t launch_generic(const LaunchPlan &pl, const EngDev &E, const P
 static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, int mode, double *out_dev, cudaStream_t st,
                          bool allow_mma = true) {
   LaunchPlan pl;
+  if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
   if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;
@@ -469,7 +471,7 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   CU(cudaMemsetAsync(D.c, 0, sizeof(double2) * n, st));
   CU(cudaMemsetAsync(D.sign, 0, sizeof(double) * n, st));
   const double inv2pid = std::pow(2.0 * M_PI, -(double)d);
-  k_init_records<<<(n + 127) / 128, 128, 0, st>>>(D, zi, probi, e->oiA, e->oiB, e->oiC, e->cfg.oi0_fac, inv2pid, zt, wvi);
+  k_init_records<<<(n < e->sm_count * 16 ? n : e->sm_count * 16), 128, 0, st>>>(D, zi, probi, e->oiA, e->oiB, e->oiC, e->cfg.oi0_fac, inv2pid, zt, wvi);
   CU(cudaGetLastError());
   e->launches += 1;
   // prefactor at t = 0 initialises the branch trackers (propagators.py:628-631)

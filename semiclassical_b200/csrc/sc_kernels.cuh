@@ -13,6 +13,9 @@
 // to the product in flight; kv_{s-1} is recovered from them when U_{s+1} is formed.
 #pragma once
 #include "sc_device.cuh"
+#ifndef SC_MAX_DIM
+#define SC_MAX_DIM 64
+#endif
 
 namespace sc {
 
@@ -31,7 +34,7 @@ __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ld
   int o = 0;
   L.off_Ub = o; o += d * ldu;
   L.off_Vb = o; o += d * ldu;
-  int us = d * ldu;
+  int us = ((d + 3) & ~3) * ldu;           // rows padded to the k-step of the tensor-core variant
   if (us < 2 * dr * dr) us = 2 * dr * dr;   // Us doubles as the complex prefactor matrix
   L.off_Us = o; o += us;
   int hs = ((d + 7) & ~7) * ldh;            // rows padded to 8 for the tensor-core variant
@@ -39,7 +42,7 @@ __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ld
   L.off_H = o; o += hs;
   L.off_vec = o; o += 8 * L.dpad + 8;       // q, p, qs, g, scr, scr2, dqv, dpv + scalars
   L.off_red = o; o += 8 * 32;               // cross-warp reduction scratch
-  L.off_int = o; o += (dr + 6) & ~1;        // LU bookkeeping (2 dr ints) + pivot inverse (double2)
+  L.off_int = o; o += (dr < 32 ? 38 : (dr + 6) & ~1);  // LU bookkeeping (2 dr ints | 64 keys) + pivot inverse (double2)
   L.total = (o + 1) & ~1;
   return L;
 }
@@ -164,7 +167,8 @@ k_hk_generic(EngDev E, PotDev P, double h, int nsteps, int mode, double *partial
       double2 det = make_double2(0.0, 0.0);
       if (mode != MODE_CORR) {
         prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, H, t, gid);
-        det = lu_det<TPT>(Cm, dr, ibuf, pivbuf, t, gid);
+        if (TPT == 32) det = lu_det<TPT>(Cm, dr, ibuf, pivbuf, t, gid);
+        else det = lu_det_cta<(TPT == 32 ? 64 : TPT)>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
       }
       // ================= correlation contributions =================
       double v8[8];
@@ -232,40 +236,56 @@ __global__ void k_reduce_partials(const double *partials, int ngroups, int nstep
 
 // ensemble installation: zi (2d, n) batch-last -> trajectory-major records with Mqq = Mpp = 1, S = 0;
 // also the time-independent overlap <qi,pi,Gi|q0,p0,G0> / (probi (2 pi)^d)   (propagators.py:581-603, 795, 837)
+// One CTA per trajectory (grid-stride): record writes are coalesced, the overlap is reduced by warp 0.
 __global__ void k_init_records(EngDev E, const double *zi, const double *probi, const double *oiA, const double *oiB,
                                const double *oiC, double oi_fac, double inv2pid, double *zt_out, double2 *wvi_out) {
-  const int traj = blockIdx.x * blockDim.x + threadIdx.x;
-  if (traj >= E.n) return;
-  const int d = E.d, n = E.n;
-  double *rec = E.rec + (size_t)traj * E.rs;
-  double *zt = zt_out + (size_t)traj * 2 * d;
-  for (int k = 0; k < 2 * d; ++k) { const double z = zi[(size_t)k * n + traj]; zt[k] = z; rec[k] = z; }
-  rec[2 * d] = 0.0;
-  const int NE = 2 * d * d, W = 2 * d;
-  for (int idx = 0; idx < NE; ++idx) {
-    const int a = idx / W, b = idx % W;
-    rec[E.qps + idx] = (b == a) ? 1.0 : 0.0;            // U = [1 | 0]
-    rec[E.qps + NE + idx] = (b == d + a) ? 1.0 : 0.0;   // V = [0 | 1]
-  }
-  // overlap with bra = (qi, pi, Gamma_i), ket = (q0, p0, Gamma_0)
-  double re = 0.0, im = 0.0;
-  for (int a = 0; a < d; ++a) {
-    const double dq = E.q0[a] - zt[a], dpa = E.p0[a] - zt[d + a];
-    double sa = 0.0, sb = 0.0, sc_ = 0.0;
-    if (E.diag) {
-      sa = oiA[a] * dq; sb = oiB[a] * dpa; sc_ = oiC[a] * dpa;
-    } else {
-      for (int j = 0; j < d; ++j) {
-        const double dqj = E.q0[j] - zt[j], dpj = E.p0[j] - zt[d + j];
-        sa += oiA[a * d + j] * dqj; sb += oiB[a * d + j] * dpj; sc_ += oiC[a * d + j] * dpj;
+  __shared__ double dq[SC_MAX_DIM], dpv[SC_MAX_DIM];
+  const int d = E.d, n = E.n, NE = 2 * d * d, W = 2 * d, t = threadIdx.x;
+  for (int traj = blockIdx.x; traj < n; traj += gridDim.x) {
+    double *rec = E.rec + (size_t)traj * E.rs;
+    double *zt = zt_out + (size_t)traj * 2 * d;
+    for (int k = t; k < 2 * d; k += blockDim.x) {
+      const double z = zi[(size_t)k * n + traj];
+      zt[k] = z;
+      rec[k] = z;
+      if (k < d) dq[k] = E.q0[k] - z;
+      else dpv[k - d] = E.p0[k - d] - z;
+    }
+    if (t == 0) rec[2 * d] = 0.0;
+    for (int idx = t; idx < NE; idx += blockDim.x) {
+      const int a = idx / W, b = idx % W;
+      rec[E.qps + idx] = (b == a) ? 1.0 : 0.0;            // U = [1 | 0]
+      rec[E.qps + NE + idx] = (b == d + a) ? 1.0 : 0.0;   // V = [0 | 1]
+    }
+    __syncthreads();
+    if (t < 32) {
+      // overlap with bra = (qi, pi, Gamma_i), ket = (q0, p0, Gamma_0)
+      double re = 0.0, im = 0.0;
+      for (int a = t; a < d; a += 32) {
+        double sa = 0.0, sb = 0.0, sc_ = 0.0;
+        if (E.diag) {
+          sa = oiA[a] * dq[a]; sb = oiB[a] * dpv[a]; sc_ = oiC[a] * dpv[a];
+        } else {
+          for (int j = 0; j < d; ++j) {
+            sa += oiA[a * d + j] * dq[j]; sb += oiB[a * d + j] * dpv[j]; sc_ += oiC[a * d + j] * dpv[j];
+          }
+        }
+        re += -0.5 * (dq[a] * sa + dpv[a] * sb);
+        im += -E.p0[a] * dq[a] + dq[a] * sc_;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        re += __shfl_xor_sync(0xffffffffu, re, o);
+        im += __shfl_xor_sync(0xffffffffu, im, o);
+      }
+      if (t == 0) {
+        const double2 e = cexp(re, im);
+        const double w = oi_fac * inv2pid / probi[traj];
+        wvi_out[traj] = make_double2(w * e.x, w * e.y);
       }
     }
-    re += -0.5 * (dq * sa + dpa * sb);
-    im += -E.p0[a] * dq + dq * sc_;
+    __syncthreads();
   }
-  const double2 e = cexp(re, im);
-  const double w = oi_fac * inv2pid / probi[traj];
-  wvi_out[traj] = make_double2(w * e.x, w * e.y);
 }
 
 // layout conversion: records <-> the reference's y (2d+4d^2+1, n)

@@ -1,10 +1,316 @@
-// sc_mma.cuh -- FP64 tensor-core (DMMA.8x8x4) variant of the fused Herman-Kluk step for large d.
+// sc_mma.cuh -- FP64 tensor-core variant of the fused Herman-Kluk step for large d (17 <= d <= 62).
+//
+// One CTA per trajectory, resident for K time steps.  Per RK4 stage the monodromy products
+//     [dMpq | dMpp] = -H(q_s) [Mqq | Mqp]_s            (propagators.py:347, 357; 4 d^3 flops per stage)
+// run on the FP64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4), A = H (row-major, shared), B = U_s
+// (shared), accumulators in registers.  tcgen05/TMEM has no f64 kind, so warp-level DMMA is the tensor path
+// for this problem.  Each thread owns the C-fragment elements of its warp tile for the whole step, so the RK4
+// accumulators (R1, R2 of sc_kernels.cuh) never leave registers.
+//
+// Shared-memory plan for d = 60 (bytes): Ub, Vb, Us 3 x 57 600 + H 64 x 60 x 8 = 30 720 + vectors ~= 210 KB.
+//   Ub, Vb : ld = 2d (+pad so that ld mod 16 == 8): 128-bit owner accesses are conflict-free
+//   Us     : same ld, columns XOR-swizzled by ((row>>1)&1)<<2 so that the B-fragment loads (4 k-rows x 8 columns
+//            per quarter) are conflict-free as well
+//   H      : ld mod 16 in {4, 12}: conflict-free A-fragment loads
 #pragma once
 #include "sc_kernels.cuh"
+
 namespace sc {
-static bool mma_supported(int) { return false; }
-static void mma_leading_dims(int d, int &ldu, int &ldh) { ldu = 2 * d; ldh = d; }
-static int mma_threads(int) { return 320; }
-static cudaError_t launch_mma(int, int, size_t, const EngDev &, const PotDev &, double, int, double *, const SmemLayout &,
-                              cudaStream_t) { return cudaErrorNotSupported; }
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ int swz(int row) { return ((row >> 1) & 1) << 2; }
+
+// separable potentials: thread t < d evaluates its own mode, no cross-thread dependence
+__device__ __forceinline__ double pot_local(const PotDev &P, int t, double r, double *g, double *H, int ldh) {
+  double v, hd;
+  if (P.type == POT_MORSE) {
+    if (P.all_harmonic) {
+      const double w2 = P.omega[t] * P.omega[t];
+      v = 0.5 * w2 * r * r;
+      g[t] = w2 * r;
+      hd = w2;
+    } else {
+      const double a = P.a[t], D = P.D[t];
+      const double e = exp(-a * r);
+      v = D * (1.0 - e) * (1.0 - e);
+      g[t] = 2.0 * a * D * e * (1.0 - e);
+      hd = 2.0 * a * a * D * e * (2.0 * e - 1.0);
+    }
+  } else {
+    const double eps = P.eps[t], b = P.b[t];
+    const double e1 = exp(-b * r), e2 = exp(-2.0 * b * r);
+    v = eps / (2.0 * b * b) * (1.0 - e1) * (1.0 - e1) + (1.0 - eps) * 0.5 * r * r;
+    g[t] = eps / b * (e1 - e2) + (1.0 - eps) * r;
+    hd = eps * (2.0 * e2 - e1) + (1.0 - eps);
+  }
+  H[t * ldh + t] = hd;
+  if (t == 0) v -= P.origin;
+  return v;
+}
+
+template <int WM, int WN, int NWM, int NWN>
+__global__ void __launch_bounds__(32 * NWM * NWN, 1)
+k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout L) {
+  constexpr int TPT = 32 * NWM * NWN;
+  extern __shared__ __align__(16) double smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int gg = blockIdx.x, NG = gridDim.x, gid = 0;
+  double *Ub = smem + L.off_Ub, *Vb = smem + L.off_Vb, *Us = smem + L.off_Us, *H = smem + L.off_H;
+  double *vec = smem + L.off_vec, *red = smem + L.off_red;
+  int *ibuf = reinterpret_cast<int *>(smem + L.off_int);
+  const int d = E.d, dr = E.dr, ldu = L.ldu, ldh = L.ldh, dp = L.dpad, W = 2 * d, NE = 2 * d * d;
+  const int DK = (d + 3) & ~3;
+  double *q = vec, *p = vec + dp, *qs = vec + 2 * dp, *g = vec + 3 * dp, *scr = vec + 4 * dp, *scr2 = vec + 5 * dp;
+  double *dqv = vec + 6 * dp, *dpv = vec + 7 * dp;
+  double2 *pivbuf = reinterpret_cast<double2 *>(ibuf + ((2 * dr + 3) & ~3));
+  double2 *Cm = reinterpret_cast<double2 *>(Us);
+  const double im_t = (t < d) ? P.imass[t] : 0.0;
+  const bool separable = (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
+  // warp tile origin and this thread's fragment coordinates
+  const int m0 = (warp % NWM) * WM * 8, n0 = (warp / NWM) * WN * 8;
+  const int fr = lane >> 2, fc = lane & 3;
+  // tiles of this warp that contain real columns (uniform per warp)
+  int ntile_n = 0;
+#pragma unroll
+  for (int j = 0; j < WN; ++j)
+    if (n0 + 8 * j < W) ntile_n = j + 1;
+
+  for (int traj = gg; traj < E.n; traj += NG) {
+    double *rec = E.rec + (size_t)traj * E.rs;
+    if (t < d) { q[t] = rec[t]; p[t] = rec[d + t]; }
+    double S = rec[2 * d];
+    // zero the K-padding of the operands once
+    for (int idx = t; idx < (DK - d) * ldu; idx += TPT) Us[d * ldu + idx] = 0.0;
+    for (int idx = t; idx < NE; idx += TPT) {
+      const int a = idx / W, b = idx % W;
+      const double u = rec[E.qps + idx];
+      Ub[a * ldu + b] = u;
+      Us[a * ldu + (b ^ swz(a))] = u;
+      Vb[a * ldu + b] = rec[E.qps + NE + idx];
+    }
+    double2 c2 = E.c2[traj], cc = E.c[traj];
+    double sign = E.sign[traj];
+    __syncthreads();
+
+    for (int step = 0; step < nsteps; ++step) {
+      double e4 = 0.0, accS = 0.0;
+      double R1[WM][WN][2], R2[WM][WN][2];
+      double qa = 0, pa = 0, qsa = 0, psa = 0, accq = 0, accp = 0;
+      if (t < d) { qa = q[t]; pa = p[t]; qsa = qa; psa = pa; qs[t] = qa; }
+      // H: zero / constant part (the dense prefactor assembly uses H as scratch, so refill every step)
+      double vpart = 0.0;
+      if (separable) {
+        for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
+        __syncthreads();
+        if (t < d) vpart = pot_local(P, t, qsa, g, H, ldh);
+        __syncthreads();
+      } else {
+        for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
+        __syncthreads();
+        vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, true);
+      }
+#pragma unroll 1
+      for (int s = 1; s <= 4; ++s) {
+        const double cnext = (s == 3) ? h : 0.5 * h;
+        const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
+        // ---- phase A: acc = H U_s on the tensor pipe
+        double acc[WM][WN][2];
+#pragma unroll
+        for (int i = 0; i < WM; ++i)
+#pragma unroll
+          for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        {
+          const double *Ha = H + (m0 + fr) * ldh + fc;
+#pragma unroll 3
+          for (int k0 = 0; k0 < DK; k0 += 4) {
+            double a[WM], b[WN];
+            const int krow = k0 + fc;
+            const double *Ur = Us + krow * ldu;
+            const int sw = swz(krow);
+#pragma unroll
+            for (int i = 0; i < WM; ++i) a[i] = Ha[i * 8 * ldh + k0];
+#pragma unroll
+            for (int j = 0; j < WN; ++j) b[j] = (j < ntile_n) ? Ur[(n0 + 8 * j + fr) ^ sw] : 0.0;
+#pragma unroll
+            for (int i = 0; i < WM; ++i)
+#pragma unroll
+              for (int j = 0; j < WN; ++j)
+                if (j < ntile_n) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          }
+        }
+        double kq = 0, kp = 0;
+        if (t < d) {
+          kq = psa * im_t;
+          kp = -g[t];
+          const double tk = 0.5 * psa * psa * im_t;
+          accS += wgt * (tk - vpart);
+          if (s == 4) e4 = tk + vpart;
+        }
+        __syncthreads();
+        // ---- phase B: RK4 accumulators (kv = -acc), operand of the next stage, vector part
+#pragma unroll
+        for (int i = 0; i < WM; ++i) {
+          const int a = m0 + 8 * i + fr;
+          const double ima = (a < d) ? P.imass[a] : 0.0;
+          const int sw = swz(a);
+#pragma unroll
+          for (int j = 0; j < WN; ++j) {
+            const int b = n0 + 8 * j + 2 * fc;
+            if (a < d && b < W) {
+              const double2 ub = *reinterpret_cast<const double2 *>(Ub + a * ldu + b);
+              const double2 vb = *reinterpret_cast<const double2 *>(Vb + a * ldu + b);
+              const double k0v = -acc[i][j][0], k1v = -acc[i][j][1];
+              double2 un;
+              if (s == 1) {
+                R1[i][j][0] = k0v; R1[i][j][1] = k1v;
+                R2[i][j][0] = 0.0; R2[i][j][1] = 0.0;
+                un.x = ub.x + 0.5 * h * vb.x * ima;
+                un.y = ub.y + 0.5 * h * vb.y * ima;
+              } else if (s == 2) {
+                un.x = ub.x + 0.5 * h * (vb.x + 0.5 * h * R1[i][j][0]) * ima;
+                un.y = ub.y + 0.5 * h * (vb.y + 0.5 * h * R1[i][j][1]) * ima;
+                R1[i][j][0] += k0v; R1[i][j][1] += k1v;
+                R2[i][j][0] = k0v; R2[i][j][1] = k1v;
+              } else if (s == 3) {
+                un.x = ub.x + h * (vb.x + 0.5 * h * R2[i][j][0]) * ima;
+                un.y = ub.y + h * (vb.y + 0.5 * h * R2[i][j][1]) * ima;
+                R1[i][j][0] += k0v; R1[i][j][1] += k1v;
+                R2[i][j][0] += k0v; R2[i][j][1] += k1v;
+              } else {
+                R2[i][j][0] += k0v; R2[i][j][1] += k1v;
+                un.x = ub.x + h * vb.x * ima + (h * h / 6.0) * R1[i][j][0] * ima;
+                un.y = ub.y + h * vb.y * ima + (h * h / 6.0) * R1[i][j][1] * ima;
+                double2 vn;
+                vn.x = vb.x + (h / 6.0) * (R1[i][j][0] + R2[i][j][0]);
+                vn.y = vb.y + (h / 6.0) * (R1[i][j][1] + R2[i][j][1]);
+                *reinterpret_cast<double2 *>(Ub + a * ldu + b) = un;
+                *reinterpret_cast<double2 *>(Vb + a * ldu + b) = vn;
+              }
+              *reinterpret_cast<double2 *>(Us + a * ldu + (b ^ sw)) = un;  // U_{s+1}; after stage 4: U(t+h)
+            }
+          }
+        }
+        if (t < d) {
+          accq += wgt * kq;
+          accp += wgt * kp;
+          if (s < 4) {
+            qsa = qa + cnext * kq;
+            psa = pa + cnext * kp;
+            qs[t] = qsa;
+            if (separable) vpart = pot_local(P, t, qsa, g, H, ldh);
+          } else {
+            qa += h / 6.0 * accq;
+            pa += h / 6.0 * accp;
+            q[t] = qa;
+            p[t] = pa;
+          }
+        }
+        __syncthreads();
+        if (s < 4 && !separable) vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, P.type == POT_ROTATED_MORSE);
+      }
+      // ================= prefactor, branch tracking, correlation contributions =================
+      prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, H, t, gid);
+      double2 det = lu_det_cta<TPT>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
+      double v8[8];
+      {
+        double v6[6];
+        corr_terms<TPT>(E, q, p, E.zt + (size_t)traj * 2 * d, dqv, dpv, v6, t, gid);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v8[i] = v6[i];
+        v8[6] = accS;
+        v8[7] = e4;
+      }
+      group_reduce<TPT, 8>(v8, red, t, gid);
+      if (t == 0) {
+        S += h / 6.0 * v8[6];
+        sign = track_sign(sign, c2, det);
+        c2 = det;
+        cc = csqrt_principal(det);
+        double2 ca, ki;
+        const double v6[6] = {v8[0], v8[1], v8[2], v8[3], v8[4], v8[5]};
+        corr_finish(E, v6, S, cc, sign, E.wvi[traj], ca, ki);
+        double *row = partials + ((size_t)gg * nsteps + step) * 5;
+        row[0] += ca.x; row[1] += ca.y; row[2] += ki.x; row[3] += ki.y; row[4] += v8[7];
+      }
+      // the LU destroyed the Us region: restore the stage-1 operand U(t+h) for the next step
+      if (step + 1 < nsteps) {
+        for (int idx = t; idx < (DK - d) * ldu; idx += TPT) Us[d * ldu + idx] = 0.0;
+        for (int idx = t; idx < d * d; idx += TPT) {
+          const int a = idx / d, b = 2 * (idx % d);
+          *reinterpret_cast<double2 *>(Us + a * ldu + (b ^ swz(a))) = *reinterpret_cast<const double2 *>(Ub + a * ldu + b);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- write back
+    if (t < d) { rec[t] = q[t]; rec[d + t] = p[t]; }
+    if (t == 0) {
+      rec[2 * d] = S;
+      E.c2[traj] = c2;
+      E.c[traj] = cc;
+      E.sign[traj] = sign;
+    }
+    for (int idx = t; idx < NE; idx += TPT) {
+      const int a = idx / W, b = idx % W;
+      rec[E.qps + idx] = Ub[a * ldu + b];
+      rec[E.qps + NE + idx] = Vb[a * ldu + b];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ host-side dispatch -------
+struct MmaConfig { int wm, wn, nwm, nwn; };
+
+static bool mma_config(int d, MmaConfig &c) {
+  if (d < 17 || d > 62) return false;
+  if (d <= 32) { c = {2, 2, 2, 4}; return true; }        //  8 warps: rows <= 32, cols <= 64
+  if (d <= 48) { c = {2, 3, 3, 4}; return true; }        // 12 warps: rows <= 48, cols <= 96
+  c = {2, 4, 4, 4};                                       // 16 warps: rows <= 64, cols <= 128
+  return true;
+}
+
+static bool mma_supported(int d) {
+  MmaConfig c;
+  return mma_config(d, c);
+}
+
+static void mma_leading_dims(int d, int &ldu, int &ldh) {
+  ldu = 2 * d;
+  while (ldu % 16 != 8) ldu += 2;      // 128-bit owner accesses conflict-free
+  const int dk = (d + 3) & ~3;
+  ldh = dk;
+  while (ldh % 16 != 4 && ldh % 16 != 12) ldh += 4;   // conflict-free A-fragment loads
+}
+
+static int mma_threads(int d) {
+  MmaConfig c;
+  mma_config(d, c);
+  return 32 * c.nwm * c.nwn;
+}
+
+template <int WM, int WN, int NWM, int NWN>
+static cudaError_t launch_mma_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps,
+                                double *partials, const SmemLayout &L, cudaStream_t st) {
+  auto kern = k_hk_mma<WM, WN, NWM, NWN>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return ce;
+  kern<<<grid, 32 * NWM * NWN, smem, st>>>(E, P, h, nsteps, partials, L);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_mma(int grid, int threads, size_t smem, const EngDev &E, const PotDev &P, double h,
+                              int nsteps, double *partials, const SmemLayout &L, cudaStream_t st) {
+  MmaConfig c;
+  if (!mma_config(E.d, c) || threads != 32 * c.nwm * c.nwn) return cudaErrorInvalidValue;
+  if (E.d <= 32) return launch_mma_t<2, 2, 2, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  if (E.d <= 48) return launch_mma_t<2, 3, 3, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  return launch_mma_t<2, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+}
+
 }  // namespace sc
