@@ -309,37 +309,52 @@ __device__ __forceinline__ double2 lu_det_cta(double2 *Cm, int dr, unsigned *wke
   }
   __syncthreads();
   for (int k = 0; k < dr; ++k) {
+    // loads that do not depend on the pivot are issued first: partial keys, this warp's rows
     const unsigned *wk = wkey + (k & 1) * 32;
     unsigned kk = (lane < NW) ? wk[lane] : 0u;
+    const int j0 = k + 1 + lane, j1 = j0 + 32;
+    const bool c0 = j0 < dr, c1 = j1 < dr;
+    double2 ak[MAXR], v0[MAXR], v1[MAXR];
+#pragma unroll
+    for (int m = 0; m < MAXR; ++m) {
+      const int i = warp + NW * m;
+      ak[m] = v0[m] = v1[m] = make_double2(0.0, 0.0);
+      if (i < dr) {
+        const double2 *row = Cm + i * dr;
+        ak[m] = row[k];
+        if (c0) v0[m] = row[j0];
+        if (c1) v1[m] = row[j1];
+      }
+    }
     kk = __reduce_max_sync(0xffffffffu, kk);
     const int p = static_cast<int>(kk & 63u);
     inversions += __popcll(done >> p);          // earlier pivots with a larger row index
     done |= 1ull << p;
-    const double2 pv = Cm[p * dr + k];
+    const double2 *prow = Cm + p * dr;
+    const double2 pv = prow[k];
+    double2 u0 = make_double2(0.0, 0.0), u1 = u0;
+    if (c0) u0 = prow[j0];
+    if (c1) u1 = prow[j1];
     det = cmul(det, pv);
     if (k + 1 == dr) break;
     const double rn = 1.0 / (pv.x * pv.x + pv.y * pv.y);
     const double2 ip = make_double2(pv.x * rn, -pv.y * rn);
-    const int j0 = k + 1 + lane, j1 = j0 + 32;
-    double2 u0 = make_double2(0.0, 0.0), u1 = u0;
-    if (j0 < dr) u0 = Cm[p * dr + j0];
-    if (j1 < dr) u1 = Cm[p * dr + j1];
     unsigned nkey = 0u;
 #pragma unroll
     for (int m = 0; m < MAXR; ++m) {
       const int i = warp + NW * m;
       if (i < dr && !((done >> i) & 1ull)) {
+        const double2 f = cmul(ak[m], ip);
         double2 *row = Cm + i * dr;
-        const double2 f = cmul(row[k], ip);
-        if (j0 < dr) {
-          double2 v = row[j0];
+        if (c0) {
+          double2 v = v0[m];
           v.x -= f.x * u0.x - f.y * u0.y;
           v.y -= f.x * u0.y + f.y * u0.x;
           row[j0] = v;
           if (lane == 0) nkey = max(nkey, pivot_key(v, i));
         }
-        if (j1 < dr) {
-          double2 v = row[j1];
+        if (c1) {
+          double2 v = v1[m];
           v.x -= f.x * u1.x - f.y * u1.y;
           v.y -= f.x * u1.y + f.y * u1.x;
           row[j1] = v;
@@ -353,19 +368,82 @@ __device__ __forceinline__ double2 lu_det_cta(double2 *Cm, int dr, unsigned *wke
   return det;
 }
 
+// Second CTA-wide variant, organised for a low instruction count (the elimination is issue-bound, not
+// flop-bound): thread (r, c) owns row r = t % 64 and the columns j == c (mod NS), NS = TPT / 64.  The row
+// stride ldc is odd (in complex elements) so that the 32 rows of a warp hit distinct banks; the pivot-row
+// element u[j] is a broadcast load.  One barrier per column as in lu_det_cta.
+template <int TPT>
+__device__ __forceinline__ double2 lu_det_rc(double2 *Cm, int dr, int ldc, unsigned *wkey, int t) {
+  static_assert(TPT % 64 == 0, "lu_det_rc needs a multiple of 64 threads");
+  constexpr int NW = TPT / 32, NS = TPT / 64;
+  const int lane = t & 31, warp = t >> 5;
+  const int r = t & 63, c = t >> 6;
+  const bool active = r < dr;
+  double2 *rowp = Cm + (active ? r : dr - 1) * ldc;
+  unsigned long long done = 0ull;
+  double2 det = make_double2(1.0, 0.0);
+  int inversions = 0;
+  {
+    unsigned key = (c == 0 && active) ? pivot_key(rowp[0], r) : 0u;
+    key = __reduce_max_sync(0xffffffffu, key);
+    if (lane == 0) wkey[warp] = key;
+  }
+  __syncthreads();
+  for (int k = 0; k < dr; ++k) {
+    const unsigned *wk = wkey + (k & 1) * 32;
+    unsigned kk = (lane < NW) ? wk[lane] : 0u;
+    const double2 ak = rowp[k];
+    kk = __reduce_max_sync(0xffffffffu, kk);
+    const int p = static_cast<int>(kk & 63u);
+    inversions += __popcll(done >> p);          // earlier pivots with a larger row index
+    done |= 1ull << p;
+    const double2 *prow = Cm + p * ldc;
+    const double2 pv = prow[k];
+    det = cmul(det, pv);
+    if (k + 1 == dr) break;
+    const double rn = 1.0 / (pv.x * pv.x + pv.y * pv.y);
+    const double2 f = cmul(ak, make_double2(pv.x * rn, -pv.y * rn));
+    const bool mine = active && !((done >> r) & 1ull);
+    // first owned column beyond k
+    int j = c + NS * ((k + 1 - c + NS - 1 >= 0 ? (k + 1 - c + NS - 1) : 0) / NS);
+    unsigned nkey = 0u;
+    if (j == k + 1) {
+      const double2 u = prow[j];
+      double2 v = rowp[j];
+      v.x -= f.x * u.x - f.y * u.y;
+      v.y -= f.x * u.y + f.y * u.x;
+      if (mine) { rowp[j] = v; nkey = pivot_key(v, r); }
+      j += NS;
+    }
+#pragma unroll 2
+    for (; j < dr; j += NS) {
+      const double2 u = prow[j];
+      double2 v = rowp[j];
+      v.x -= f.x * u.x - f.y * u.y;
+      v.y -= f.x * u.y + f.y * u.x;
+      if (mine) rowp[j] = v;
+    }
+    nkey = __reduce_max_sync(0xffffffffu, nkey);
+    if (lane == 0) wkey[((k + 1) & 1) * 32 + warp] = nkey;
+    __syncthreads();
+  }
+  if (inversions & 1) { det.x = -det.x; det.y = -det.y; }
+  return det;
+}
+
 // ------------------------------------------------------------------ prefactor assembly -------
 // Cm (dr x dr complex) = 1/2 [ L1 Mqq R1 + L2 Mpp R2 - i L1 Mqp R2 + i L2 Mpq R1 ]     (propagators.py:969-994)
 // Ub = [Mqq|Mqp], Vb = [Mpq|Mpp] (d x 2d, ld = ldu) in shared memory; T: shared scratch d x dr.
 template <int TPT>
 __device__ __forceinline__ void prefactor_assemble(const EngDev &E, const double *Ub, const double *Vb, int ldu,
-                                                   double2 *Cm, double *T, int t, int gid) {
+                                                   double2 *Cm, int ldc, double *T, int t, int gid) {
   const int d = E.d, dr = E.dr;
   if (E.diag) {
     for (int idx = t; idx < d * d; idx += TPT) {
       const int a = idx / d, b = idx % d;
       const double mqq = Ub[a * ldu + b], mqp = Ub[a * ldu + d + b], mpq = Vb[a * ldu + b], mpp = Vb[a * ldu + d + b];
       const double sa = E.sgt[a], isa = E.isgt[a], sb = E.sgi[b], isb = E.isgi[b];
-      Cm[idx] = make_double2(0.5 * (sa * mqq * isb + isa * mpp * sb), 0.5 * (-sa * mqp * sb + isa * mpq * isb));
+      Cm[a * ldc + b] = make_double2(0.5 * (sa * mqq * isb + isa * mpp * sb), 0.5 * (-sa * mqp * sb + isa * mpq * isb));
     }
     Group<TPT>::sync(gid);
     return;
@@ -388,11 +466,11 @@ __device__ __forceinline__ void prefactor_assemble(const EngDev &E, const double
       double s = 0.0;
       for (int a = 0; a < d; ++a) s += __ldg(L + ap * d + a) * T[a * dr + bp];
       s *= 0.5;
-      double2 v = (blk == 0) ? make_double2(0.0, 0.0) : Cm[idx];
+      double2 v = (blk == 0) ? make_double2(0.0, 0.0) : Cm[ap * ldc + bp];
       if (blk < 2) v.x += s;
       else if (blk == 2) v.y -= s;
       else v.y += s;
-      Cm[idx] = v;
+      Cm[ap * ldc + bp] = v;
     }
     Group<TPT>::sync(gid);
   }

@@ -619,3 +619,16 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
 
 // ------------------------------------------------------------------ generic-potential stage path
 #include "sc_stage.cuh"
+
+// ------------------------------------------------------------------ diagnostics
+#ifdef SC_PHASE_TIMING
+extern "C" int sc_debug_phase_cycles(unsigned long long *out16, int reset) {
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out16, sc::g_phase_cycles, sizeof(unsigned long long) * 16));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    CU(cudaMemcpyToSymbol(sc::g_phase_cycles, z, sizeof(z)));
+  }
+  return SC_OK;
+}
+#endif

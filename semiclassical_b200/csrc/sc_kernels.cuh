@@ -35,7 +35,7 @@ __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ld
   L.off_Ub = o; o += d * ldu;
   L.off_Vb = o; o += d * ldu;
   int us = ((d + 3) & ~3) * ldu;           // rows padded to the k-step of the tensor-core variant
-  if (us < 2 * dr * dr) us = 2 * dr * dr;   // Us doubles as the complex prefactor matrix
+  if (us < 2 * dr * (dr + 1)) us = 2 * dr * (dr + 1);   // Us doubles as the complex prefactor matrix (odd row stride)
   L.off_Us = o; o += us;
   int hs = ((d + 7) & ~7) * ldh;            // rows padded to 8 for the tensor-core variant
   if (hs < d * dr) hs = d * dr;             // H doubles as the T scratch of the prefactor assembly
@@ -166,7 +166,7 @@ k_hk_generic(EngDev E, PotDev P, double h, int nsteps, int mode, double *partial
       // ================= prefactor + branch tracking =================
       double2 det = make_double2(0.0, 0.0);
       if (mode != MODE_CORR) {
-        prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, H, t, gid);
+        prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, dr, H, t, gid);
         if (TPT == 32) det = lu_det<TPT>(Cm, dr, ibuf, pivbuf, t, gid);
         else det = lu_det_cta<(TPT == 32 ? 64 : TPT)>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
       }

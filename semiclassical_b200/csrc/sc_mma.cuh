@@ -53,6 +53,16 @@ __device__ __forceinline__ double pot_local(const PotDev &P, int t, double r, do
   return v;
 }
 
+// optional phase timing (compile with -DSC_PHASE_TIMING): thread 0 of CTA 0 accumulates clock64() deltas
+#ifdef SC_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[16];
+#define PT_DECL long long pt_last = clock64();
+#define PT(idx) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = clock64(); g_phase_cycles[idx] += (unsigned long long)(now_ - pt_last); pt_last = now_; } } while (0)
+#else
+#define PT_DECL
+#define PT(idx) do { } while (0)
+#endif
+
 template <int WM, int WN, int NWM, int NWN>
 __global__ void __launch_bounds__(32 * NWM * NWN, 1)
 k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout L) {
@@ -74,12 +84,13 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
   // warp tile origin and this thread's fragment coordinates
   const int m0 = (warp % NWM) * WM * 8, n0 = (warp / NWM) * WN * 8;
   const int fr = lane >> 2, fc = lane & 3;
-  // tiles of this warp that contain real columns (uniform per warp)
-  int ntile_n = 0;
+  // swizzled B-fragment columns of this thread (loop invariant: the k-row parity bit is fc's); tiles that lie
+  // entirely in the column padding read column 0 and produce ignored results
+  int bcol[WN];
 #pragma unroll
-  for (int j = 0; j < WN; ++j)
-    if (n0 + 8 * j < W) ntile_n = j + 1;
+  for (int j = 0; j < WN; ++j) bcol[j] = ((n0 + 8 * j < W) ? (n0 + 8 * j + fr) : 0) ^ swz(fc);
 
+  PT_DECL
   for (int traj = gg; traj < E.n; traj += NG) {
     double *rec = E.rec + (size_t)traj * E.rs;
     if (t < d) { q[t] = rec[t]; p[t] = rec[d + t]; }
@@ -96,6 +107,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
     double2 c2 = E.c2[traj], cc = E.c[traj];
     double sign = E.sign[traj];
     __syncthreads();
+    PT(0);
 
     for (int step = 0; step < nsteps; ++step) {
       double e4 = 0.0, accS = 0.0;
@@ -105,8 +117,10 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
       // H: zero / constant part (the dense prefactor assembly uses H as scratch, so refill every step)
       double vpart = 0.0;
       if (separable) {
-        for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
-        __syncthreads();
+        if (step == 0 || !E.diag) {
+          for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
+          __syncthreads();
+        }
         if (t < d) vpart = pot_local(P, t, qsa, g, H, ldh);
         __syncthreads();
       } else {
@@ -114,11 +128,12 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
         __syncthreads();
         vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, true);
       }
+      PT(1);
 #pragma unroll 1
       for (int s = 1; s <= 4; ++s) {
         const double cnext = (s == 3) ? h : 0.5 * h;
         const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
-        // ---- phase A: acc = H U_s on the tensor pipe
+        // ---- phase A: acc = H U_s on the tensor pipe (software-pipelined fragment loads)
         double acc[WM][WN][2];
 #pragma unroll
         for (int i = 0; i < WM; ++i)
@@ -126,21 +141,33 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
           for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
         {
           const double *Ha = H + (m0 + fr) * ldh + fc;
-#pragma unroll 3
-          for (int k0 = 0; k0 < DK; k0 += 4) {
-            double a[WM], b[WN];
-            const int krow = k0 + fc;
-            const double *Ur = Us + krow * ldu;
-            const int sw = swz(krow);
+          const double *Bp = Us + fc * ldu;
+          const int ldu4 = 4 * ldu, ldh8 = 8 * ldh;
+          double a[WM], b[WN];
 #pragma unroll
-            for (int i = 0; i < WM; ++i) a[i] = Ha[i * 8 * ldh + k0];
+          for (int i = 0; i < WM; ++i) a[i] = Ha[i * ldh8];
 #pragma unroll
-            for (int j = 0; j < WN; ++j) b[j] = (j < ntile_n) ? Ur[(n0 + 8 * j + fr) ^ sw] : 0.0;
+          for (int j = 0; j < WN; ++j) b[j] = Bp[bcol[j]];
+          const int nk = DK >> 2;
+#pragma unroll 5
+          for (int k = 1; k <= nk; ++k) {
+            double an[WM], bn[WN];
+            if (k < nk) {
+              Ha += 4;
+              Bp += ldu4;
+#pragma unroll
+              for (int i = 0; i < WM; ++i) an[i] = Ha[i * ldh8];
+#pragma unroll
+              for (int j = 0; j < WN; ++j) bn[j] = Bp[bcol[j]];
+            }
 #pragma unroll
             for (int i = 0; i < WM; ++i)
 #pragma unroll
-              for (int j = 0; j < WN; ++j)
-                if (j < ntile_n) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+              for (int j = 0; j < WN; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+#pragma unroll
+            for (int i = 0; i < WM; ++i) a[i] = an[i];
+#pragma unroll
+            for (int j = 0; j < WN; ++j) b[j] = bn[j];
           }
         }
         double kq = 0, kp = 0;
@@ -152,6 +179,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
           if (s == 4) e4 = tk + vpart;
         }
         __syncthreads();
+        PT(2);
         // ---- phase B: RK4 accumulators (kv = -acc), operand of the next stage, vector part
 #pragma unroll
         for (int i = 0; i < WM; ++i) {
@@ -211,11 +239,17 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
           }
         }
         __syncthreads();
+        PT(3);
         if (s < 4 && !separable) vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, P.type == POT_ROTATED_MORSE);
+        PT(1);
       }
       // ================= prefactor, branch tracking, correlation contributions =================
-      prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, H, t, gid);
-      double2 det = lu_det_cta<TPT>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
+      const int ldc = dr | 1;
+      prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, ldc, H, t, gid);
+      PT(4);
+      double2 det = (TPT % 64 == 0) ? lu_det_rc<(TPT % 64 == 0 ? TPT : 64)>(Cm, dr, ldc, reinterpret_cast<unsigned *>(ibuf), t)
+                                    : lu_det_cta<TPT>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
+      PT(5);
       double v8[8];
       {
         double v6[6];
@@ -237,6 +271,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
         double *row = partials + ((size_t)gg * nsteps + step) * 5;
         row[0] += ca.x; row[1] += ca.y; row[2] += ki.x; row[3] += ki.y; row[4] += v8[7];
       }
+      PT(6);
       // the LU destroyed the Us region: restore the stage-1 operand U(t+h) for the next step
       if (step + 1 < nsteps) {
         for (int idx = t; idx < (DK - d) * ldu; idx += TPT) Us[d * ldu + idx] = 0.0;
@@ -246,6 +281,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
         }
       }
       __syncthreads();
+      PT(7);
     }
     // ---- write back
     if (t < d) { rec[t] = q[t]; rec[d + t] = p[t]; }
@@ -261,6 +297,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
       rec[E.qps + NE + idx] = Vb[a * ldu + b];
     }
     __syncthreads();
+    PT(8);
   }
 }
 
@@ -271,6 +308,7 @@ static bool mma_config(int d, MmaConfig &c) {
   if (d < 17 || d > 62) return false;
   if (d <= 32) { c = {2, 2, 2, 4}; return true; }        //  8 warps: rows <= 32, cols <= 64
   if (d <= 48) { c = {2, 3, 3, 4}; return true; }        // 12 warps: rows <= 48, cols <= 96
+  if (d <= 60) { c = {2, 5, 4, 3}; return true; }        // 12 warps: rows <= 64, cols <= 120 (d = 60: no padding)
   c = {2, 4, 4, 4};                                       // 16 warps: rows <= 64, cols <= 128
   return true;
 }
@@ -310,6 +348,7 @@ static cudaError_t launch_mma(int grid, int threads, size_t smem, const EngDev &
   if (!mma_config(E.d, c) || threads != 32 * c.nwm * c.nwn) return cudaErrorInvalidValue;
   if (E.d <= 32) return launch_mma_t<2, 2, 2, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
   if (E.d <= 48) return launch_mma_t<2, 3, 3, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  if (E.d <= 60) return launch_mma_t<2, 5, 4, 3>(grid, smem, E, P, h, nsteps, partials, L, st);
   return launch_mma_t<2, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
 }
 
