@@ -358,7 +358,7 @@ static int plan_launch(const sc_engine *e, int mode, bool allow_mma, LaunchPlan 
       pl.tpt = pl.threads = mma_threads(d);
     }
   }
-  pl.L = make_layout(d, dr, ldu, ldh);
+  pl.L = make_layout(d, dr, ldu, ldh, pl.mma ? MMA_KMAX : 0);
   pl.smem = sizeof(double) * (size_t)pl.L.total * pl.groups_per_cta;
   if (pl.smem > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "shared-memory footprint %zu B exceeds 227 KB (d = %d)", pl.smem, d);
   const int groups_needed = n;
@@ -400,11 +400,12 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
     CU(cudaMalloc(&e->partials, sizeof(double) * need));
     e->partials_cap = need;
   }
-  if (mode != MODE_INIT) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
+  if (mode != MODE_INIT && !pl.mma) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
   cudaError_t ce = cudaSuccess;
   if (pl.mma) {
     ce = launch_mma(pl.grid, pl.threads, pl.smem, e->dev, P, h, nsteps, e->partials, pl.L, st);
     e->kernel_name = "k_hk_mma";
+    e->launches += (nsteps - 1) / MMA_KMAX;
   } else {
     e->kernel_name = "k_hk_generic";
 #define CASE(T, E_) ce = launch_generic<T, E_>(pl, e->dev, P, h, nsteps, mode, e->partials, st)

@@ -23,10 +23,12 @@ enum KernelMode { MODE_STEP = 0, MODE_INIT = 1, MODE_CORR = 2 };
 
 struct SmemLayout {
   int ldu, ldh, dpad;
-  int off_Ub, off_Vb, off_Us, off_H, off_vec, off_red, off_int, total;  // in doubles, per group
+  int off_Ub, off_Vb, off_Us, off_H, off_vec, off_red, off_int, off_lu, off_acc, total;  // in doubles, per group
 };
 
-__host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ldh) {
+// mma_kmax > 0: layout of the tensor-core kernel (register LU exchange area, shared correlation accumulators
+// for mma_kmax time steps per launch)
+__host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ldh, int mma_kmax = 0) {
   SmemLayout L;
   L.ldu = ldu;
   L.ldh = ldh;
@@ -40,9 +42,16 @@ __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ld
   int hs = ((d + 7) & ~7) * ldh;            // rows padded to 8 for the tensor-core variant
   if (hs < d * dr) hs = d * dr;             // H doubles as the T scratch of the prefactor assembly
   L.off_H = o; o += hs;
-  L.off_vec = o; o += 8 * L.dpad + 8;       // q, p, qs, g, scr, scr2, dqv, dpv + scalars
+  L.off_vec = o; o += 14 * L.dpad + 8;      // q, p, qs, g, scr, scr2, dqv, dpv, 4 Hessian diagonals, 2 stashes
   L.off_red = o; o += 8 * 32;               // cross-warp reduction scratch
   L.off_int = o; o += (dr < 32 ? 38 : (dr + 6) & ~1);  // LU bookkeeping (2 dr ints | 64 keys) + pivot inverse (double2)
+  o = (o + 1) & ~1;
+  L.off_lu = o; L.off_acc = o;
+  if (mma_kmax > 0) {
+    o += (int)((sizeof(LuShared) + 7) / 8);
+    o = (o + 1) & ~1;
+    L.off_acc = o; o += 5 * mma_kmax;
+  }
   L.total = (o + 1) & ~1;
   return L;
 }

@@ -63,21 +63,49 @@ __device__ unsigned long long g_phase_cycles[16];
 #define PT(idx) do { } while (0)
 #endif
 
-template <int WM, int WN, int NWM, int NWN>
+constexpr int MMA_KMAX = 128;   // time steps per launch (size of the shared correlation accumulators)
+
+// separable potentials without side effects: value, gradient and Hessian diagonal of mode t at r
+__device__ __forceinline__ double pot_local_vals(const PotDev &P, int t, double r, double &gout, double &hd) {
+  double v;
+  if (P.type == POT_MORSE) {
+    if (P.all_harmonic) {
+      const double w2 = P.omega[t] * P.omega[t];
+      v = 0.5 * w2 * r * r;
+      gout = w2 * r;
+      hd = w2;
+    } else {
+      const double a = P.a[t], D = P.D[t];
+      const double e = exp(-a * r);
+      v = D * (1.0 - e) * (1.0 - e);
+      gout = 2.0 * a * D * e * (1.0 - e);
+      hd = 2.0 * a * a * D * e * (2.0 * e - 1.0);
+    }
+  } else {
+    const double eps = P.eps[t], b = P.b[t];
+    const double e1 = exp(-b * r), e2 = exp(-2.0 * b * r);
+    v = eps / (2.0 * b * b) * (1.0 - e1) * (1.0 - e1) + (1.0 - eps) * 0.5 * r * r;
+    gout = eps / b * (e1 - e2) + (1.0 - eps) * r;
+    hd = eps * (2.0 * e2 - e1) + (1.0 - eps);
+  }
+  if (t == 0) v -= P.origin;
+  return v;
+}
+
+template <int WM, int WN, int NWM, int NWN, int MC>
 __global__ void __launch_bounds__(32 * NWM * NWN, 1)
-k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout L) {
-  constexpr int TPT = 32 * NWM * NWN;
+k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, double *partials, SmemLayout L) {
+  constexpr int NW = NWM * NWN, TPT = 32 * NW;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int gg = blockIdx.x, NG = gridDim.x, gid = 0;
   double *Ub = smem + L.off_Ub, *Vb = smem + L.off_Vb, *Us = smem + L.off_Us, *H = smem + L.off_H;
-  double *vec = smem + L.off_vec, *red = smem + L.off_red;
-  int *ibuf = reinterpret_cast<int *>(smem + L.off_int);
+  double *vec = smem + L.off_vec, *red = smem + L.off_red, *cacc = smem + L.off_acc;
+  LuShared *lush = reinterpret_cast<LuShared *>(smem + L.off_lu);
   const int d = E.d, dr = E.dr, ldu = L.ldu, ldh = L.ldh, dp = L.dpad, W = 2 * d, NE = 2 * d * d;
   const int DK = (d + 3) & ~3;
   double *q = vec, *p = vec + dp, *qs = vec + 2 * dp, *g = vec + 3 * dp, *scr = vec + 4 * dp, *scr2 = vec + 5 * dp;
-  double *dqv = vec + 6 * dp, *dpv = vec + 7 * dp;
-  double2 *pivbuf = reinterpret_cast<double2 *>(ibuf + ((2 * dr + 3) & ~3));
+  double *dqv = vec + 6 * dp, *dpv = vec + 7 * dp, *hdv = vec + 8 * dp, *sacc = vec + 12 * dp, *se4 = vec + 13 * dp;
   double2 *Cm = reinterpret_cast<double2 *>(Us);
   const double im_t = (t < d) ? P.imass[t] : 0.0;
   const bool separable = (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
@@ -90,6 +118,8 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
 #pragma unroll
   for (int j = 0; j < WN; ++j) bcol[j] = ((n0 + 8 * j < W) ? (n0 + 8 * j + fr) : 0) ^ swz(fc);
 
+  for (int i = t; i < 5 * nsteps; i += TPT) cacc[i] = 0.0;
+  for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
   PT_DECL
   for (int traj = gg; traj < E.n; traj += NG) {
     double *rec = E.rec + (size_t)traj * E.rs;
@@ -106,6 +136,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
     }
     double2 c2 = E.c2[traj], cc = E.c[traj];
     double sign = E.sign[traj];
+    const double2 wvi = E.wvi[traj];
     __syncthreads();
     PT(0);
 
@@ -113,17 +144,40 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
       double e4 = 0.0, accS = 0.0;
       double R1[WM][WN][2], R2[WM][WN][2];
       double qa = 0, pa = 0, qsa = 0, psa = 0, accq = 0, accp = 0;
-      if (t < d) { qa = q[t]; pa = p[t]; qsa = qa; psa = pa; qs[t] = qa; }
-      // H: zero / constant part (the dense prefactor assembly uses H as scratch, so refill every step)
       double vpart = 0.0;
       if (separable) {
-        if (step == 0 || !E.diag) {
-          for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
-          __syncthreads();
+        // (q, p) do not depend on the monodromy blocks: run their whole RK4 step now and keep the four
+        // Hessian diagonals for the matrix stages
+        if (t < d) {
+          qa = q[t]; pa = p[t]; qsa = qa; psa = pa;
+#pragma unroll
+          for (int s = 1; s <= 4; ++s) {
+            const double cnext = (s == 3) ? h : 0.5 * h;
+            const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
+            double gt, hd;
+            vpart = pot_local_vals(P, t, qsa, gt, hd);
+            hdv[(s - 1) * dp + t] = hd;
+            const double kq = psa * im_t, kp = -gt;
+            const double tk = 0.5 * psa * psa * im_t;
+            accS += wgt * (tk - vpart);
+            if (s == 4) e4 = tk + vpart;
+            accq += wgt * kq;
+            accp += wgt * kp;
+            if (s < 4) {
+              qsa = qa + cnext * kq;
+              psa = pa + cnext * kp;
+            }
+          }
+          q[t] = qa + h / 6.0 * accq;
+          p[t] = pa + h / 6.0 * accp;
+          sacc[t] = accS;
+          se4[t] = e4;
+          H[t * ldh + t] = hdv[t];
         }
-        if (t < d) vpart = pot_local(P, t, qsa, g, H, ldh);
         __syncthreads();
       } else {
+        if (t < d) { qa = q[t]; pa = p[t]; qsa = qa; psa = pa; qs[t] = qa; }
+        // the dense prefactor assembly uses H as scratch: refill every step
         for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
         __syncthreads();
         vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, true);
@@ -171,7 +225,7 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
           }
         }
         double kq = 0, kp = 0;
-        if (t < d) {
+        if (!separable && t < d) {
           kq = psa * im_t;
           kp = -g[t];
           const double tk = 0.5 * psa * psa * im_t;
@@ -224,18 +278,21 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
           }
         }
         if (t < d) {
-          accq += wgt * kq;
-          accp += wgt * kp;
-          if (s < 4) {
-            qsa = qa + cnext * kq;
-            psa = pa + cnext * kp;
-            qs[t] = qsa;
-            if (separable) vpart = pot_local(P, t, qsa, g, H, ldh);
+          if (separable) {
+            if (s < 4) H[t * ldh + t] = hdv[s * dp + t];
           } else {
-            qa += h / 6.0 * accq;
-            pa += h / 6.0 * accp;
-            q[t] = qa;
-            p[t] = pa;
+            accq += wgt * kq;
+            accp += wgt * kp;
+            if (s < 4) {
+              qsa = qa + cnext * kq;
+              psa = pa + cnext * kp;
+              qs[t] = qsa;
+            } else {
+              qa += h / 6.0 * accq;
+              pa += h / 6.0 * accp;
+              q[t] = qa;
+              p[t] = pa;
+            }
           }
         }
         __syncthreads();
@@ -243,44 +300,94 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
         if (s < 4 && !separable) vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, P.type == POT_ROTATED_MORSE);
         PT(1);
       }
-      // ================= prefactor, branch tracking, correlation contributions =================
-      const int ldc = dr | 1;
-      prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, ldc, H, t, gid);
-      PT(4);
-      double2 det = (TPT % 64 == 0) ? lu_det_rc<(TPT % 64 == 0 ? TPT : 64)>(Cm, dr, ldc, reinterpret_cast<unsigned *>(ibuf), t)
-                                    : lu_det_cta<TPT>(Cm, dr, reinterpret_cast<unsigned *>(ibuf), t);
-      PT(5);
-      double v8[8];
+      if (separable && t < d) { accS = sacc[t]; e4 = se4[t]; }
+      // ================= correlation partial sums (need only q, p): reduced by warps 0 and 1, consumed by
+      // thread 0 after the LU, whose barriers order the shared-memory traffic =================
       {
+        double v8[8];
         double v6[6];
         corr_terms<TPT>(E, q, p, E.zt + (size_t)traj * 2 * d, dqv, dpv, v6, t, gid);
+        if (warp < 2) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) v8[i] = v6[i];
-        v8[6] = accS;
-        v8[7] = e4;
+          for (int i = 0; i < 6; ++i) v8[i] = v6[i];
+          v8[6] = accS;
+          v8[7] = e4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v8[i] += __shfl_xor_sync(0xffffffffu, v8[i], o);
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) red[i * 2 + warp] = v8[i];
+          }
+        }
       }
-      group_reduce<TPT, 8>(v8, red, t, gid);
+      // ================= prefactor: assembly into registers (transposed: det A^T = det A), LU =================
+      double2 lo[MC], hi[MC];
+      if (E.diag) {
+        const double sb0 = (lane < d) ? E.sgi[lane] : 0.0, isb0 = (lane < d) ? E.isgi[lane] : 0.0;
+        const double sb1 = (lane + 32 < d) ? E.sgi[lane + 32] : 0.0, isb1 = (lane + 32 < d) ? E.isgi[lane + 32] : 0.0;
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+          const int a = warp + NW * m;
+          lo[m] = hi[m] = make_double2(0.0, 0.0);
+          if (a < d) {
+            const double sa = 0.5 * E.sgt[a], isa = 0.5 * E.isgt[a];
+            const double *ur = Ub + a * ldu, *vr = Vb + a * ldu;
+            if (lane < d)
+              lo[m] = make_double2(sa * ur[lane] * isb0 + isa * vr[d + lane] * sb0,
+                                   -sa * ur[d + lane] * sb0 + isa * vr[lane] * isb0);
+            if (lane + 32 < d)
+              hi[m] = make_double2(sa * ur[lane + 32] * isb1 + isa * vr[d + lane + 32] * sb1,
+                                   -sa * ur[d + lane + 32] * sb1 + isa * vr[lane + 32] * isb1);
+          }
+        }
+      } else {
+        const int ldc = dr | 1;
+        prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, ldc, H, t, gid);
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+          const int a = warp + NW * m;
+          lo[m] = hi[m] = make_double2(0.0, 0.0);
+          if (a < dr) {
+            if (lane < dr) lo[m] = Cm[a * ldc + lane];
+            if (lane + 32 < dr) hi[m] = Cm[a * ldc + lane + 32];
+          }
+        }
+      }
+      PT(4);
+      const double2 det = lu_det_regs<NW, MC, 0>(lo, hi, dr, lush, warp, lane);
+      PT(5);
       if (t == 0) {
-        S += h / 6.0 * v8[6];
+        double v6[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v6[i] = red[i * 2] + red[i * 2 + 1];
+        S += h / 6.0 * (red[12] + red[13]);
         sign = track_sign(sign, c2, det);
         c2 = det;
         cc = csqrt_principal(det);
         double2 ca, ki;
-        const double v6[6] = {v8[0], v8[1], v8[2], v8[3], v8[4], v8[5]};
-        corr_finish(E, v6, S, cc, sign, E.wvi[traj], ca, ki);
-        double *row = partials + ((size_t)gg * nsteps + step) * 5;
-        row[0] += ca.x; row[1] += ca.y; row[2] += ki.x; row[3] += ki.y; row[4] += v8[7];
+        corr_finish(E, v6, S, cc, sign, wvi, ca, ki);
+        double *row = cacc + step * 5;
+        row[0] += ca.x; row[1] += ca.y; row[2] += ki.x; row[3] += ki.y; row[4] += red[14] + red[15];
       }
       PT(6);
-      // the LU destroyed the Us region: restore the stage-1 operand U(t+h) for the next step
-      if (step + 1 < nsteps) {
-        for (int idx = t; idx < (DK - d) * ldu; idx += TPT) Us[d * ldu + idx] = 0.0;
-        for (int idx = t; idx < d * d; idx += TPT) {
-          const int a = idx / d, b = 2 * (idx % d);
-          *reinterpret_cast<double2 *>(Us + a * ldu + (b ^ swz(a))) = *reinterpret_cast<const double2 *>(Ub + a * ldu + b);
+      if (!E.diag) {
+        // the dense assembly used the Us region for the prefactor matrix and H as scratch: restore the stage-1
+        // operand U(t+h) for the next step
+        __syncthreads();
+        if (step + 1 < nsteps) {
+          for (int idx = t; idx < (DK - d) * ldu; idx += TPT) Us[d * ldu + idx] = 0.0;
+          for (int idx = t; idx < d * d; idx += TPT) {
+            const int a = idx / d, b = 2 * (idx % d);
+            *reinterpret_cast<double2 *>(Us + a * ldu + (b ^ swz(a))) = *reinterpret_cast<const double2 *>(Ub + a * ldu + b);
+          }
         }
+        if (separable)
+          for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
+        __syncthreads();
       }
-      __syncthreads();
       PT(7);
     }
     // ---- write back
@@ -299,6 +406,9 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, double *partials, SmemLayout 
     __syncthreads();
     PT(8);
   }
+  // per-CTA correlation sums of this launch (each row is written by exactly one CTA: no memset, no atomics)
+  for (int i = t; i < 5 * nsteps; i += TPT)
+    partials[((size_t)gg * nsteps_total + step0 + i / 5) * 5 + i % 5] = cacc[i];
 }
 
 // ------------------------------------------------------------------ host-side dispatch -------
@@ -332,24 +442,30 @@ static int mma_threads(int d) {
   return 32 * c.nwm * c.nwn;
 }
 
-template <int WM, int WN, int NWM, int NWN>
+template <int WM, int WN, int NWM, int NWN, int MC>
 static cudaError_t launch_mma_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps,
                                 double *partials, const SmemLayout &L, cudaStream_t st) {
-  auto kern = k_hk_mma<WM, WN, NWM, NWN>;
+  auto kern = k_hk_mma<WM, WN, NWM, NWN, MC>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  kern<<<grid, 32 * NWM * NWN, smem, st>>>(E, P, h, nsteps, partials, L);
-  return cudaGetLastError();
+  for (int s0 = 0; s0 < nsteps; s0 += MMA_KMAX) {
+    const int ns = (nsteps - s0 < MMA_KMAX) ? nsteps - s0 : MMA_KMAX;
+    kern<<<grid, 32 * NWM * NWN, smem, st>>>(E, P, h, ns, s0, nsteps, partials, L);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return ce;
+  }
+  return cudaSuccess;
 }
 
 static cudaError_t launch_mma(int grid, int threads, size_t smem, const EngDev &E, const PotDev &P, double h,
                               int nsteps, double *partials, const SmemLayout &L, cudaStream_t st) {
   MmaConfig c;
   if (!mma_config(E.d, c) || threads != 32 * c.nwm * c.nwn) return cudaErrorInvalidValue;
-  if (E.d <= 32) return launch_mma_t<2, 2, 2, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
-  if (E.d <= 48) return launch_mma_t<2, 3, 3, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
-  if (E.d <= 60) return launch_mma_t<2, 5, 4, 3>(grid, smem, E, P, h, nsteps, partials, L, st);
-  return launch_mma_t<2, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  // last parameter: LU columns per thread = ceil(max d of the bucket / warps)
+  if (E.d <= 32) return launch_mma_t<2, 2, 2, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  if (E.d <= 48) return launch_mma_t<2, 3, 3, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  if (E.d <= 60) return launch_mma_t<2, 5, 4, 3, 5>(grid, smem, E, P, h, nsteps, partials, L, st);
+  return launch_mma_t<2, 4, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
 }
 
 }  // namespace sc
