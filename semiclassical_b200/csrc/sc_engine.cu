@@ -41,7 +41,14 @@ extern "C" const char *sc_last_error(void) { return g_err.c_str(); }
 // ------------------------------------------------------------------ device buffers ----------
 struct DevPool {
   std::vector<void *> ptrs;
-  ~DevPool() { for (void *p : ptrs) cudaFree(p); }
+  DevPool() = default;
+  DevPool(const DevPool &) = delete;
+  DevPool &operator=(const DevPool &) = delete;
+  ~DevPool() { release(); }
+  void release() {
+    for (void *p : ptrs) cudaFree(p);
+    ptrs.clear();
+  }
   cudaError_t upload(const double *host, size_t n, const double **out) {
     double *p = nullptr;
     cudaError_t e = cudaMalloc(&p, sizeof(double) * (n ? n : 1));
@@ -60,6 +67,15 @@ struct DevPool {
     *out = reinterpret_cast<T *>(p);
     return e;
   }
+};
+
+// ------------------------------------------------------------------ Walton-Manolopoulos host state
+struct WMState {
+  WMDev dev;
+  WMLayout L;
+  double *n1_dev = nullptr, *scratch5 = nullptr, *partials = nullptr;
+  int tpt = 32, groups = 1, grid = 1;
+  size_t smem = 0;
 };
 
 struct sc_potential {
@@ -210,6 +226,111 @@ extern "C" int sc_potential_eval(const sc_potential *pot, int n, const double *r
   return SC_OK;
 }
 
+
+// ------------------------------------------------------------------ Walton-Manolopoulos dispatch
+// constants of propagators.py:1102-1130 and the trajectory-independent matrices of eqns (68, 69)
+static int wm_setup(WMState &w, const sc_engine_config &cfg, DevPool &pool) {
+  const int d = cfg.d, dr = cfg.dr;
+  const size_t dd = (size_t)d * d;
+  if (!cfg.iGamma_0 || !cfg.U) return fail(SC_ERR_INVALID, "WM needs iGamma_0 and U");
+  w.dev = WMDev();
+  w.dev.d = d;
+  w.dev.dr = dr;
+  w.dev.alpha = cfg.alpha;
+  w.dev.beta = cfg.beta;
+  w.dev.pref = std::sqrt(cfg.detG0) * std::pow(cfg.detGt, 0.25) * std::pow(cfg.detGi, 0.25) / std::sqrt(cfg.detGi0);
+  std::vector<double> GiG(dd, 0.0), Cqq(dd, 0.0);
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += cfg.Gamma_0[i * d + k] * cfg.iGi0[k * d + j];
+      GiG[i * d + j] = s;
+    }
+  for (int i = 0; i < d; ++i)
+    for (int j = 0; j < d; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s += GiG[i * d + k] * cfg.Gamma_0[k * d + j];
+      Cqq[i * d + j] = cfg.Gamma_0[i * d + j] - s;
+    }
+  CU(pool.upload(cfg.Gamma_0, dd, &w.dev.G0));
+  CU(pool.upload(cfg.Gamma_i, dd, &w.dev.Gi));
+  CU(pool.upload(cfg.Gamma_t, dd, &w.dev.Gt));
+  CU(pool.upload(cfg.iGi0, dd, &w.dev.iGi0));
+  CU(pool.upload(cfg.iGamma_0, dd, &w.dev.iG0));
+  CU(pool.upload(GiG.data(), dd, &w.dev.GiG));
+  CU(pool.upload(Cqq.data(), dd, &w.dev.Cqq));
+  CU(pool.upload(cfg.U, (size_t)d * dr, &w.dev.U));
+  CU(pool.alloc((size_t)d, &w.n1_dev));
+  CU(cudaMemset(w.n1_dev, 0, sizeof(double) * d));
+  w.dev.n1 = w.n1_dev;
+  w.L = make_wm_layout(d, dr);
+  const size_t ws = sizeof(double2) * (size_t)w.L.total;
+  if (d <= 8) {
+    w.tpt = 32;
+    w.groups = (int)((200 * 1024) / ws);
+    if (w.groups > 4) w.groups = 4;
+    if (w.groups < 1) w.groups = 1;
+  } else {
+    w.tpt = 128;
+    w.groups = 1;
+  }
+  w.smem = ws * w.groups;
+  if (w.smem > 227 * 1024)
+    return fail(SC_ERR_UNSUPPORTED, "Walton-Manolopoulos workspace %zu B exceeds 227 KB of shared memory (d = %d)", w.smem, d);
+  return SC_OK;
+}
+
+static int wm_set_nac(WMState &w, const double *n1, int d) {
+  CU(cudaMemcpy(w.n1_dev, n1, sizeof(double) * d, cudaMemcpyHostToDevice));
+  return SC_OK;
+}
+
+static int wm_alloc(WMState &w, DevPool &ens, const EngDev &D, const double *q0_dev, const double *p0_dev,
+                    const double *probi_dev, int sm_count, cudaStream_t st) {
+  const int n = D.n;
+  double *winv = nullptr;
+  CU(ens.alloc((size_t)n, &w.dev.prevA));
+  CU(ens.alloc((size_t)n, &w.dev.prevM));
+  CU(ens.alloc((size_t)n, &w.dev.signA));
+  CU(ens.alloc((size_t)n, &w.dev.signM));
+  CU(ens.alloc((size_t)n, &winv));
+  CU(ens.alloc((size_t)8, &w.scratch5));
+  w.dev.winv = winv;
+  w.dev.q0 = q0_dev;
+  w.dev.p0 = p0_dev;
+  int per_sm = (int)((227 * 1024) / (w.smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2048 / (w.tpt * w.groups)) per_sm = 2048 / (w.tpt * w.groups);
+  int grid = sm_count * per_sm;
+  const int need = (n + w.groups - 1) / w.groups;
+  if (grid > need) grid = need;
+  w.grid = grid < 1 ? 1 : grid;
+  CU(ens.alloc((size_t)w.grid * w.groups * 4, &w.partials));
+  k_wm_winv<<<(n + 255) / 256, 256, 0, st>>>(probi_dev, std::pow(2.0 * M_PI, -(double)D.d), n, winv);
+  CU(cudaGetLastError());
+  return SC_OK;
+}
+
+// mode WM_INIT: prefactor pieces + tracker initialisation; WM_STEP: + tracker update + contributions;
+// WM_CORR: contributions only (trackers untouched).  out5: device, [0..3] correlation sums, [4] <- energy_src[4]
+static int wm_launch(WMState &w, const EngDev &D, int mode, double inv_norm, double *out5, const double *energy_src,
+                     cudaStream_t st) {
+  const int threads = w.tpt * w.groups;
+  if (w.tpt == 32) {
+    CU(cudaFuncSetAttribute(k_wm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<32><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
+  } else {
+    CU(cudaFuncSetAttribute(k_wm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<128><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
+  }
+  CU(cudaGetLastError());
+  if (mode != WM_INIT) {
+    k_wm_reduce<<<1, 160, 0, st>>>(w.partials, w.grid * w.groups, inv_norm, energy_src, out5);
+    CU(cudaGetLastError());
+  }
+  return SC_OK;
+}
+
 // ------------------------------------------------------------------ engine ------------------
 static bool is_diagonal(const double *A, int d) {
   for (int i = 0; i < d; ++i)
@@ -290,7 +411,7 @@ extern "C" int sc_engine_create(sc_engine **out, const sc_engine_config *cfg) {
   D.wG = e->d_wG;
   if (cfg->wm) {
     int rc = wm_setup(e->wm, *cfg, e->pool);
-    if (rc) { delete e; return fail(SC_ERR_CUDA, "WM constant upload failed"); }
+    if (rc) { delete e; return rc; }
   }
 #undef UP
   // the config's pointers are the caller's; never dereference them after create
@@ -329,7 +450,8 @@ static int set_nac(sc_engine *e, const double *n1, cudaStream_t st) {
   CU(cudaMemcpy(e->d_wG, w.data() + d, sizeof(double) * d, cudaMemcpyHostToDevice));
   e->dev.p0n1 = p0n1;
   e->nac_cache.assign(n1, n1 + d);
-  if (e->cfg.wm) wm_set_nac(e->wm, n1, d);
+  if (e->cfg.wm)
+    if (int rc = wm_set_nac(e->wm, n1, d)) return rc;
   return SC_OK;
 }
 
@@ -400,7 +522,7 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
     CU(cudaMalloc(&e->partials, sizeof(double) * need));
     e->partials_cap = need;
   }
-  if (mode != MODE_INIT && !pl.mma) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
+  if (mode != MODE_INIT && mode != MODE_TRACK && !pl.mma) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
   cudaError_t ce = cudaSuccess;
   if (pl.mma) {
     ce = launch_mma(pl.grid, pl.threads, pl.smem, e->dev, P, h, nsteps, e->partials, pl.L, st);
@@ -424,7 +546,7 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
   }
   if (ce != cudaSuccess) return fail(SC_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(ce));
   e->launches += 1;
-  if (mode != MODE_INIT) {
+  if (mode != MODE_INIT && mode != MODE_TRACK) {
     k_reduce_partials<<<nrows, 160, 0, st>>>(e->partials, ngroups, nrows, 1.0 / (double)e->ntraj_norm,
                                              1.0 / (double)e->dev.n, out_dev);
     CU(cudaGetLastError());
@@ -453,7 +575,8 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   EngDev &D = e->dev;
   const int d = D.d;
   CU(cudaStreamSynchronize(st));
-  e->ens = DevPool();  // releases the previous ensemble
+  e->ens.release();  // the previous ensemble
+  e->stage_buf = nullptr;
   D.n = n;
   D.qps = (2 * d + 1 + 1) & ~1;
   D.rs = D.qps + 4 * d * d;
@@ -481,9 +604,9 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   none.imass = D.q0;  // never dereferenced beyond d entries in MODE_INIT
   if (int rc = run_hk_kernel(e, none, 0.0, 0, MODE_INIT, nullptr, st)) return rc;
   if (e->cfg.wm) {
-    if (int rc = wm_alloc(e->wm, e->ens, D, st)) return fail(SC_ERR_CUDA, "WM allocation failed");
-    if (int rc = wm_prefactor_launch(e->wm, D, /*init=*/1, st)) return fail(SC_ERR_CUDA, "WM prefactor launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    e->launches += 1;
+    if (int rc = wm_alloc(e->wm, e->ens, D, D.q0, D.p0, probi, e->sm_count, st)) return rc;
+    if (int rc = wm_launch(e->wm, e->dev, WM_INIT, 0.0, nullptr, nullptr, st)) return rc;
+    e->launches += 2;
   }
   return SC_OK;
 }
@@ -527,11 +650,8 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
   // Walton-Manolopoulos: the HK kernel advances the trajectories one step at a time, the WM kernel evaluates
   // the Filinov-smoothed prefactor pieces and the WM contributions of every new time
   for (int k = 0; k < nsteps; ++k) {
-    if (int rc = ensure_corr(e, 1, st)) return rc;
     if (int rc = run_hk_kernel(e, pot->dev, dt, 1, MODE_STEP, e->wm.scratch5, st)) return rc;
-    if (wm_prefactor_launch(e->wm, e->dev, 0, st)) return fail(SC_ERR_CUDA, "WM prefactor launch failed");
-    if (wm_corr_launch(e->wm, e->dev, pot->dev, 1.0 / (double)e->ntraj_norm, corr_dev + 5 * k, e->wm.scratch5, st))
-      return fail(SC_ERR_CUDA, "WM correlation launch failed");
+    if (int rc = wm_launch(e->wm, e->dev, WM_STEP, 1.0 / (double)e->ntraj_norm, corr_dev + 5 * k, e->wm.scratch5, st)) return rc;
     e->launches += 2;
   }
   return SC_OK;
@@ -556,9 +676,8 @@ static int correlations_impl(sc_engine *e, const PotDev &P, const double *n1, do
   if (!e->cfg.wm) {
     if (int rc = run_hk_kernel(e, P, 0.0, 1, MODE_CORR, e->corr_dev, st)) return rc;
   } else {
-    if (wm_corr_launch(e->wm, e->dev, P, 1.0 / (double)e->ntraj_norm, e->corr_dev, nullptr, st))
-      return fail(SC_ERR_CUDA, "WM correlation launch failed");
-    e->launches += 1;
+    if (int rc = wm_launch(e->wm, e->dev, WM_CORR, 1.0 / (double)e->ntraj_norm, e->corr_dev, nullptr, st)) return rc;
+    e->launches += 2;
   }
   CU(cudaMemcpyAsync(out_host, e->corr_dev, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -607,8 +726,8 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
   if (signs) {
     CU(cudaMemcpyAsync(signs, e->dev.sign, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     if (e->cfg.wm) {
-      CU(cudaMemcpyAsync(signs + n, e->wm.signA, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-      CU(cudaMemcpyAsync(signs + 2 * n, e->wm.signM, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(signs + n, e->wm.dev.signA, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(signs + 2 * n, e->wm.dev.signM, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     } else {
       std::vector<double> ones(2 * (size_t)n, 1.0);
       CU(cudaMemcpyAsync(signs + n, ones.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));

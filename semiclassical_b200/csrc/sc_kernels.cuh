@@ -19,7 +19,7 @@
 
 namespace sc {
 
-enum KernelMode { MODE_STEP = 0, MODE_INIT = 1, MODE_CORR = 2 };
+enum KernelMode { MODE_STEP = 0, MODE_INIT = 1, MODE_CORR = 2, MODE_TRACK = 3 };  // TRACK: prefactor + branch tracking only
 
 struct SmemLayout {
   int ldu, ldh, dpad;
@@ -191,7 +191,7 @@ k_hk_generic(EngDev E, PotDev P, double h, int nsteps, int mode, double *partial
       }
       group_reduce<TPT, 8>(v8, red, t, gid);
       if (t == 0) {
-        if (mode == MODE_STEP) {
+        if (mode == MODE_STEP || mode == MODE_TRACK) {
           S += h / 6.0 * v8[6];
           sign = track_sign(sign, c2, det);
           c2 = det;
@@ -201,7 +201,7 @@ k_hk_generic(EngDev E, PotDev P, double h, int nsteps, int mode, double *partial
           c2 = det;
           cc = csqrt_principal(det);
         }
-        if (mode != MODE_INIT) {
+        if (mode != MODE_INIT && mode != MODE_TRACK) {
           double2 ca, ki;
           const double v6[6] = {v8[0], v8[1], v8[2], v8[3], v8[4], v8[5]};
           corr_finish(E, v6, S, cc, sign, E.wvi[traj], ca, ki);

@@ -8,7 +8,7 @@
 // tracks the sqrt branches of det A and det M and reduces the contributions.
 //
 // The per-trajectory routine is __host__ __device__: tests/emul compiles it for the host with one "thread"
-// per group so that the formulas are checked against the oracle on machines without a GPU.
+// per group so that the formulas can be checked on machines without a GPU.
 //
 // Note on eqn (55): as coded in the reference b0 = gradL - i (Mqz^T P - Eqz^T p) with gradL = i (Mqz^T P - Eqz^T p)
 // (propagators.py:1167-1180, 1262-1264), i.e. b0 vanishes identically; the terms it multiplies (the b0 parts of

@@ -43,6 +43,7 @@ def _stream_ptr(device):
 class _NativePotential(object):
     """owns one sc_potential handle per CUDA device (created on first use on that device)"""
     _origin = 0.0
+    _fused_step = True   # evaluated inside the fused step kernels (False: batched kernel + stage interface)
 
     def _create(self, out):
         raise NotImplementedError
@@ -244,6 +245,8 @@ class MolecularHarmonicPotential(_MolecularPotentialBase):
 
 class MolecularGDMLPotential(_MolecularPotentialBase):
     """sGDML ground-state surface with analytic Hessians (potentials.py:641-744, gdml_predictor.py:35-250)"""
+    _fused_step = False
+
     def __init__(self, model_pot, nac_fchk):
         model = dict(model_pot)
         assert np.array_equal(model['z'], nac_fchk.atomic_numbers()), \

@@ -267,6 +267,12 @@ class HermanKlukPropagator(object):
         handle = getattr(potential, '_handle', None)
         return handle(self.device) if handle is not None else None
 
+    def _fused_potential(self, potential):
+        """handle of a potential the fused step kernels evaluate in-kernel, else None (stage interface)"""
+        if not getattr(potential, '_fused_step', True):
+            return None
+        return self._native_potential(potential)
+
     def _check_energy(self, energies, change_tol=1.0e-2):
         """<T+V> (4th RK4 stage) must not change by more than change_tol between steps (propagators.py:385-398)"""
         for en in energies:
@@ -282,7 +288,7 @@ class HermanKlukPropagator(object):
         """propagates the ensemble for one time step (t -> t+dt) under the influence of `potential`"""
         assert self.dim == potential.dimensions(), "potential has wrong dimensions"
         h = float(dt)
-        handle = self._native_potential(potential)
+        handle = self._fused_potential(potential)
         if handle is None:
             self._step_generic(potential, h)
         else:
@@ -300,9 +306,15 @@ class HermanKlukPropagator(object):
         e^{i t E0 / hbar} phase -- the same numbers nsteps x {step; autocorrelation; ic_correlation} produce.
         """
         assert self.dim == potential.dimensions(), "potential has wrong dimensions"
-        handle = self._native_potential(potential)
+        handle = self._fused_potential(potential)
         if handle is None:
-            raise NotImplementedError("propagate() needs a native potential; generic potentials go through step()")
+            # potentials evaluated outside the fused kernels (Python objects, sGDML): step by step
+            auto, ic = np.zeros(nsteps, complex), np.zeros(nsteps, complex)
+            for k in range(nsteps):
+                self.step(potential, dt)
+                auto[k] = self.autocorrelation(energy0_es)
+                ic[k] = self.ic_correlation(potential, energy0_es)
+            return auto, ic
         h = float(dt)
         out = np.zeros((nsteps, 5))
         with torch.cuda.device(self.device):

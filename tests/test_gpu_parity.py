@@ -128,3 +128,125 @@ def test_wrong_dimension_is_rejected(cuda_device):
     pot5 = helpers.potential_from_golden(helpers.load_golden("hk_as5_chi002"))
     with pytest.raises(AssertionError):
         pr.step(pot5, 0.1)
+
+
+# ------------------------------------------------------------------ Walton-Manolopoulos (config 2)
+WM_GOLDENS = ["wm_1d", "wm_as5_chi002", "wm_as5_rot", "wm_methylium"]
+
+
+def _check_wm_signs(pr, g):
+    st = pr.sign_trackers
+    assert np.array_equal(st["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
+    assert np.array_equal(st["detA"]["signs"].real.cpu().numpy(), g['signs_detA'].real)
+    assert np.array_equal(st["detM"]["signs"].real.cpu().numpy(), g['signs_detM'].real)
+
+
+@pytest.mark.parametrize("name", WM_GOLDENS)
+def test_wm_step_loop_matches_reference(name, cuda_device):
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    auto, ic = run_loop(pr, pot, float(g['dt']), int(g['nt']), float(g['energy0_es']))
+    assert relerr(auto, g['autocorrelation']) < TOL
+    assert relerr(ic, g['ic_correlation']) < TOL
+    nk = g['y_final'].shape[1]
+    assert relerr(pr.y[:, :nk].cpu().numpy(), g['y_final']) < TOL
+    _check_wm_signs(pr, g)
+
+
+@pytest.mark.parametrize("name", WM_GOLDENS)
+def test_wm_fused_propagate_matches_reference(name, cuda_device):
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    nt, e0 = int(g['nt']), float(g['energy0_es'])
+    a0, i0 = pr.autocorrelation(e0), pr.ic_correlation(pot, e0)
+    a, i = pr.propagate(pot, float(g['dt']), nt - 1, e0)
+    assert relerr(np.concatenate(([a0], a)), g['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), g['ic_correlation']) < TOL
+    pr.step(pot, float(g['dt']))
+    _check_wm_signs(pr, g)
+
+
+# ------------------------------------------------------------------ sGDML (config 5)
+# the kernel sum over training points is cancellation-prone: the reference's own gradient / Hessian move by
+# ~3e-9 (absolute) when the training set is summed in another order; the kernel's
+# summation order differs from torch's, hence the looser potential-level tolerance.
+GDML_TOL = 1.0e-8
+
+
+@pytest.mark.parametrize("name,kwargs", [("gdml_pot_n17", {}), ("gdml_pot_n5", dict(n_atoms=5, n_train=16, sig=10, seed=3))])
+def test_gdml_kernel_matches_reference(name, kwargs, cuda_device):
+    from semiclassical_b200 import workloads, potentials
+    model, pos = workloads.gdml_synthetic(**kwargs)
+    g = helpers.load_golden(name)
+    d = len(pos)
+    pot = potentials.MolecularGDMLPotential.from_arrays(model, np.ones(d), np.zeros(d))
+    r = T(g['r'].T.copy()).to(cuda_device)
+    V, grad, hess = pot.harmonic_approximation(r)
+    V, grad, hess = V.cpu().numpy(), grad.cpu().numpy(), hess.cpu().numpy()
+    assert np.abs(V - g['energy']).max() < GDML_TOL * max(1.0, np.abs(g['energy']).max())
+    assert relerr(grad.T, g['grad']) < GDML_TOL
+    assert relerr(hess.transpose(2, 0, 1), g['hess']) < GDML_TOL
+    assert np.abs(hess - hess.transpose(1, 0, 2)).max() < 1.0e-13 * np.abs(hess).max()
+
+
+def test_gdml_kernel_large_batch_against_oracle(cuda_device):
+    """1000 geometries (several per CTA, every tile phase exercised) vs the C oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials
+    model, pos = workloads.gdml_synthetic()
+    d = len(pos)
+    rng = np.random.default_rng(5)
+    r = pos[:, None] + 0.05 * rng.standard_normal((d, 1000))
+    opot = oracle.Potential.gdml(model, np.ones(d), np.zeros(d))
+    Vo, go, ho = opot.eval(r)
+    pot = potentials.MolecularGDMLPotential.from_arrays(model, np.ones(d), np.zeros(d))
+    V, grad, hess = pot.harmonic_approximation(T(r).to(cuda_device))
+    assert np.abs(V.cpu().numpy() - Vo).max() < GDML_TOL * max(1.0, np.abs(Vo).max())
+    assert relerr(grad.cpu().numpy(), go) < GDML_TOL
+    assert relerr(hess.cpu().numpy(), ho) < GDML_TOL
+
+
+def test_hk_with_gdml_potential_matches_reference(cuda_device):
+    """HK dynamics driven by the sGDML kernel through the stage interface (4-atom fixture, 200 trajectories)"""
+    g = helpers.load_golden("hk_gdml4")
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    auto, ic = run_loop(pr, pot, float(g['dt']), int(g['nt']), float(g['energy0_es']))
+    assert relerr(auto, g['autocorrelation']) < 1.0e-8
+    assert relerr(ic, g['ic_correlation']) < 1.0e-8
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
+
+
+# ------------------------------------------------------------------ generic-potential stage interface
+class _PythonPotential(object):
+    """duck-typed potential (no native handle): the protocol of SURVEY.md section 8b"""
+    def __init__(self, inner):
+        self.inner = inner
+
+    def dimensions(self):
+        return self.inner.dimensions()
+
+    def masses(self):
+        return self.inner.masses()
+
+    def harmonic_approximation(self, r):
+        return self.inner.harmonic_approximation(r)
+
+    def derivative_coupling_1st(self, r):
+        return self.inner.derivative_coupling_1st(r)
+
+    def derivative_coupling_2nd(self, r):
+        return self.inner.derivative_coupling_2nd(r)
+
+
+@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium", "hk_as24_rot", "wm_as5_rot"])
+def test_python_potential_through_stage_interface(name, cuda_device):
+    g = helpers.load_golden(name)
+    pot = _PythonPotential(helpers.potential_from_golden(g))
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    nt = min(int(g['nt']), 40)
+    auto, ic = run_loop(pr, pot, float(g['dt']), nt, float(g['energy0_es']))
+    assert relerr(auto, g['autocorrelation'][:nt]) < TOL
+    assert relerr(ic, g['ic_correlation'][:nt]) < TOL
