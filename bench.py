@@ -175,7 +175,8 @@ def main():
 
     T = lambda x: torch.from_numpy(np.ascontiguousarray(x))  # noqa: E731
     n_total = args.ntraj
-    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    from semiclassical_b200 import distributed
+    lo, hi = distributed.shard_bounds(n_total, rank, world)
     n_local = hi - lo
     if Q is None:
         pot = potentials.MorsePotential(T(model.omega), T(model.chi), T(model.nac))
@@ -197,13 +198,9 @@ def main():
                         ntraj_total=n_total)
 
     def run_steps(nsteps):
-        auto, ic = pr.propagate(pot, dt, nsteps, model.en_zpt)
-        if dist is not None:
-            buf = torch.from_numpy(np.stack((auto.real, auto.imag, ic.real, ic.imag))).to(device)
-            dist.all_reduce(buf)
-            buf = buf.cpu().numpy()
-            auto, ic = buf[0] + 1j * buf[1], buf[2] + 1j * buf[3]
-        return auto, ic
+        # K fused steps; for N > 1 the (K, 5) buffer of per-step sums is all-reduced on the device (NCCL) before
+        # the single device->host copy
+        return pr.propagate(pot, dt, nsteps, model.en_zpt, group=True if dist is not None else None)
 
     def barrier():
         if dist is not None:
@@ -218,6 +215,10 @@ def main():
         return float(t.item())
 
     c0 = pr.autocorrelation(model.en_zpt)
+    if dist is not None:   # every rank holds its shard's share of C(0)
+        t0 = torch.tensor([c0.real, c0.imag], device=device)
+        dist.all_reduce(t0)
+        c0 = complex(float(t0[0]), float(t0[1]))
     for _ in range(W):
         run_steps(1)
     sampler = ClockSampler(local_rank)

@@ -299,37 +299,48 @@ class HermanKlukPropagator(object):
             self._corr_cache = (potential, out[0] + 1j * out[1], out[2] + 1j * out[3])
         self.t += dt
 
-    def propagate(self, potential, dt, nsteps, energy0_es=0.0):
+    def propagate(self, potential, dt, nsteps, energy0_es=0.0, group=None):
         """
         nsteps fused time steps in one launch.  Returns (autocorrelation, ic_correlation), complex arrays of
         length nsteps holding the values at the nsteps NEW times t+dt ... t+nsteps*dt, including the
         e^{i t E0 / hbar} phase -- the same numbers nsteps x {step; autocorrelation; ic_correlation} produce.
+
+        group : torch.distributed process group (or True for the default group) when this propagator holds one
+                shard of a global ensemble: the per-step sums are combined by ONE all-reduce on the device
+                (semiclassical_b200.distributed) before they are copied to the host.
         """
         assert self.dim == potential.dimensions(), "potential has wrong dimensions"
         handle = self._fused_potential(potential)
         if handle is None:
             # potentials evaluated outside the fused kernels (Python objects, sGDML): step by step
+            assert group is None, "sharded propagation needs a potential the fused kernels evaluate"
             auto, ic = np.zeros(nsteps, complex), np.zeros(nsteps, complex)
             for k in range(nsteps):
                 self.step(potential, dt)
                 auto[k] = self.autocorrelation(energy0_es)
                 ic[k] = self.ic_correlation(potential, energy0_es)
             return auto, ic
+        from semiclassical_b200 import distributed
         h = float(dt)
-        out = np.zeros((nsteps, 5))
+        rows = torch.empty((nsteps, 5), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _native.check(_native.lib().sc_engine_step(self._engine, handle, h, nsteps, out.ctypes.data, self._stream()))
-        self._check_energy(out[:, 4])
+            _native.check(_native.lib().sc_engine_step_dev(self._engine, handle, h, nsteps, rows.data_ptr(), self._stream()))
+            local_energy = rows[:, 4].clone() if group is not None else None
+            if group is not None:
+                distributed.allreduce_rows(rows, self.ntraj, self.ntraj_total, None if group is True else group)
+            out = rows.cpu().numpy()
+        self._check_energy(out[:, 4] if local_energy is None else local_energy.cpu().numpy())
         times = np.zeros(nsteps)
         t = self.t
         for k in range(nsteps):
             t = t + dt
             times[k] = float(t)
         self.t = t
-        phase = np.exp(1j / hbar * times * energy0_es)
-        auto = (out[:, 0] + 1j * out[:, 1]) * phase
-        ic = (out[:, 2] + 1j * out[:, 3]) * phase
-        self._corr_cache = (potential, out[-1, 0] + 1j * out[-1, 1], out[-1, 2] + 1j * out[-1, 3])
+        auto, ic = distributed.rows_to_correlations(out, times, energy0_es, hbar)
+        if group is None:
+            self._corr_cache = (potential, out[-1, 0] + 1j * out[-1, 1], out[-1, 2] + 1j * out[-1, 3])
+        else:
+            self._corr_cache = None   # the cached values must stay local sums
         return auto, ic
 
     def _correlations(self, potential):
