@@ -7,12 +7,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "../../include/semiclassical_b200.h"
 #include "sc_kernels.cuh"
 #include "sc_mma.cuh"
+#include "sc_chunk.cuh"
+#include "sc_lu_batch.cuh"
 #include "sc_potentials.cuh"
 #include "sc_wm.cuh"
 
@@ -96,6 +99,8 @@ struct sc_engine {
   std::vector<double> nac_cache;
   double *partials = nullptr;
   size_t partials_cap = 0;
+  void *chunk_scratch = nullptr;   // prefactor matrices, determinants, aux rows of one batch (chunked path)
+  size_t chunk_scratch_cap = 0;
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
   long long ntraj_norm = 0;
@@ -105,6 +110,11 @@ struct sc_engine {
   WMState wm;
   // generic-potential stage path
   double *stage_buf = nullptr;
+  ~sc_engine() {
+    if (partials) cudaFree(partials);
+    if (corr_dev) cudaFree(corr_dev);
+    if (chunk_scratch) cudaFree(chunk_scratch);
+  }
 };
 
 // ------------------------------------------------------------------ potentials --------------
@@ -507,10 +517,82 @@ static cudaError_t launch_generic(const LaunchPlan &pl, const EngDev &E, const P
   return cudaGetLastError();
 }
 
+static int ensure_partials(sc_engine *e, size_t need, cudaStream_t st) {
+  if (need > e->partials_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->partials) cudaFree(e->partials);
+    e->partials = nullptr;
+    CU(cudaMalloc(&e->partials, sizeof(double) * need));
+    e->partials_cap = need;
+  }
+  return SC_OK;
+}
+
+// column-chunked path (sc_chunk.cuh): RK4/monodromy kernel -> batched LU -> branch tracking + contributions,
+// batch by batch over the ensemble, KC time steps per launch
+static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
+  const int d = e->dev.d, n = e->dev.n, sm = e->sm_count;
+  const ChunkLayout L = make_chunk_layout(d);
+  const size_t smem = sizeof(double) * (size_t)L.total;
+  int KC = 8;
+  if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
+  if (KC > nsteps) KC = nsteps;
+  const int dp = (d + 1) & ~1;
+  const size_t per_traj = (size_t)KC * ((size_t)d * d * sizeof(double2) + sizeof(double2) + 8 * sizeof(double) + 4 * dp * sizeof(double));
+  size_t budget = (size_t)3 << 30;
+  if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
+  long long ntb = (long long)(budget / per_traj);
+  ntb = (ntb / sm) * sm;
+  if (ntb < sm) ntb = sm;
+  if (ntb > n) ntb = n;
+  const size_t need_bytes = per_traj * (size_t)ntb;
+  if (need_bytes > e->chunk_scratch_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
+    e->chunk_scratch = nullptr;
+    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
+    e->chunk_scratch_cap = need_bytes;
+  }
+  double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
+  double2 *det = cm + (size_t)KC * ntb * d * d;
+  double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
+  double *hd = aux + (size_t)KC * ntb * 8;
+  size_t ngroups = 0;
+  for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
+  if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
+  CU(cudaFuncSetAttribute(k_rk4_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int s0 = 0; s0 < nsteps; s0 += KC) {
+    const int ks = std::min(KC, nsteps - s0);
+    size_t g0 = 0;
+    for (long long t0 = 0; t0 < n; t0 += ntb) {
+      const int nt = (int)std::min<long long>(ntb, n - t0);
+      long long grid = (long long)nt * L.nc;
+      if (grid > 3LL * sm) grid = 3LL * sm;
+      k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
+      CU(cudaGetLastError());
+      k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
+      CU(cudaGetLastError());
+      CU(launch_lu_batch(cm, d, ks * nt, det, sm, st));
+      const int nblk = (nt + 127) / 128;
+      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
+      CU(cudaGetLastError());
+      g0 += nblk;
+      e->launches += 4;
+    }
+  }
+  k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  e->kernel_name = "k_rk4_chunk+k_lu_left+k_hk_finish";
+  return SC_OK;
+}
+
 static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, int mode, double *out_dev, cudaStream_t st,
                          bool allow_mma = true) {
   LaunchPlan pl;
   if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && chunk_supported(e->dev, P))
+    return run_hk_chunked(e, P, h, nsteps, out_dev, st);
   if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;

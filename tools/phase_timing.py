@@ -33,6 +33,9 @@ pr.propagate(pot, dt, K, m.en_zpt)
 L.sc_debug_phase_cycles(buf, 1)
 names = ["load", "potential", "gemm(4 stages)", "elementwise(4)", "prefactor assembly", "LU", "corr+reduce", "restore Us", "store"]
 ntr = (n + 147) // 148   # trajectories of CTA 0
+if pr.kernel_name().startswith("k_rk4_chunk"):
+    ntr = n * 3 / 444.0   # (trajectory, chunk) items of CTA 0
+    print("chunked path: cycles per CHUNK-step of CTA 0 (3 CTAs per SM run concurrently)")
 tot = sum(buf[:9])
 print(f"CTA 0: {ntr} trajectories x {K} steps; cycles per trajectory-step = {tot/(ntr*K):.0f}")
 for i, nm in enumerate(names):
