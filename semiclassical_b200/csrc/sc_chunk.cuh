@@ -147,6 +147,67 @@ k_qp_path(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double *
   if (lane == 0) rec[2 * d] = S;
 }
 
+// RK4 bookkeeping of one stage for the C-fragment elements of one warp (WM x WN tiles): kv = -acc, stage operand
+// formed in place (see the header).  S: stage 1..4 (compile time: straight-line code, loads batched per tile row).
+template <int S, int WM, int WN>
+__device__ __forceinline__ void chunk_phase_b(double *__restrict__ U, double *__restrict__ V, int ldu, int nb2, int d, int m0,
+                                              int fr, int fc, const double (&ima2)[WM], double h,
+                                              const double (&acc)[WM][WN][2], double (&R1)[WM][WN][2],
+                                              double (&R2)[WM][WN][2]) {
+  const double hh4 = 0.25 * h * h, hh2 = 0.5 * h * h, hh6 = h * h / 6.0, h2 = 0.5 * h, h6 = h / 6.0;
+#pragma unroll
+  for (int i = 0; i < WM; ++i) {
+    const int a = m0 + 8 * i + fr;
+    if (a < d) {
+      const double ima = ima2[i];
+      const int sw = swz(a);
+      double2 *urow = reinterpret_cast<double2 *>(U + a * ldu);
+      double2 *vrow = reinterpret_cast<double2 *>(V + a * ldu);
+      double2 u[WN], v[WN];
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int lc = 8 * j + 2 * fc;
+        u[j] = v[j] = make_double2(0.0, 0.0);
+        if (lc < nb2) {
+          u[j] = urow[(lc ^ sw) >> 1];
+          if (S != 2) v[j] = vrow[lc >> 1];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int lc = 8 * j + 2 * fc;
+        if (lc < nb2) {
+          const double k0 = -acc[i][j][0], k1 = -acc[i][j][1];
+          if (S == 1) {
+            R1[i][j][0] = k0; R1[i][j][1] = k1;
+            u[j].x = fma(h2 * ima, v[j].x, u[j].x);
+            u[j].y = fma(h2 * ima, v[j].y, u[j].y);
+          } else if (S == 2) {
+            R2[i][j][0] = k0; R2[i][j][1] = k1;
+            u[j].x = fma(hh4 * ima, R1[i][j][0], u[j].x);
+            u[j].y = fma(hh4 * ima, R1[i][j][1], u[j].y);
+          } else if (S == 3) {
+            const double a1x = R1[i][j][0], a1y = R1[i][j][1], a2x = R2[i][j][0], a2y = R2[i][j][1];
+            u[j].x += (h2 * v[j].x + hh2 * a2x - hh4 * a1x) * ima;
+            u[j].y += (h2 * v[j].y + hh2 * a2y - hh4 * a1y) * ima;
+            R1[i][j][0] = hh6 * (a1x + a2x + k0) - hh2 * a2x;
+            R1[i][j][1] = hh6 * (a1y + a2y + k1) - hh2 * a2y;
+            R2[i][j][0] = a1x + 2.0 * a2x + 2.0 * k0;
+            R2[i][j][1] = a1y + 2.0 * a2y + 2.0 * k1;
+          } else {
+            u[j].x = fma(R1[i][j][0], ima, u[j].x);
+            u[j].y = fma(R1[i][j][1], ima, u[j].y);
+            v[j].x = fma(h6, R2[i][j][0] + k0, v[j].x);
+            v[j].y = fma(h6, R2[i][j][1] + k1, v[j].y);
+            vrow[lc >> 1] = v[j];
+          }
+          urow[(lc ^ sw) >> 1] = u[j];
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(CHUNK_THREADS, 3)
 k_rk4_chunk(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
             const double *__restrict__ hd, ChunkLayout L) {
@@ -165,6 +226,9 @@ k_rk4_chunk(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
   int bcol[WN];
 #pragma unroll
   for (int j = 0; j < WN; ++j) bcol[j] = ((8 * j < 2 * nb) ? (8 * j + fr) : 0) ^ swz(fc);
+  double ima2[WM];
+#pragma unroll
+  for (int i = 0; i < WM; ++i) ima2[i] = (m0 + 8 * i + fr < d) ? P.imass[m0 + 8 * i + fr] : 0.0;
 
   for (int i = t; i < d * ldh; i += TPT) H[i] = 0.0;
   if (t < d) {
@@ -274,66 +338,11 @@ k_rk4_chunk(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
         }
         __syncthreads();
         PT(2);
-        // ---- phase B: RK4 bookkeeping, next stage operand in place (kv = -acc); loads of a whole tile row are
-        // issued before the arithmetic so that the shared-memory latency is paid once per row, not once per pair
-        const double hh4 = 0.25 * h * h, hh2 = 0.5 * h * h, hh6 = h * h / 6.0, h2 = 0.5 * h, h6 = h / 6.0;
-#pragma unroll
-        for (int i = 0; i < WM; ++i) {
-          const int a = m0 + 8 * i + fr;
-          if (a < d) {
-            const double ima = P.imass[a];
-            const int sw = swz(a);
-            double2 *urow = reinterpret_cast<double2 *>(U + a * ldu);
-            double2 *vrow = reinterpret_cast<double2 *>(V + a * ldu);
-            const bool need_v = (s != 2);
-#pragma unroll
-            for (int jg = 0; jg < WN; jg += 3) {
-              constexpr int G = 3;
-              double2 u[G], v[G];
-#pragma unroll
-              for (int jj = 0; jj < G; ++jj) {
-                const int j = jg + jj, lc = 8 * j + 2 * fc;
-                u[jj] = v[jj] = make_double2(0.0, 0.0);
-                if (j < WN && lc < 2 * nb) {
-                  u[jj] = urow[(lc ^ sw) >> 1];
-                  if (need_v) v[jj] = vrow[lc >> 1];
-                }
-              }
-#pragma unroll
-              for (int jj = 0; jj < G; ++jj) {
-                const int j = (jg + jj < WN) ? jg + jj : WN - 1, lc = 8 * (jg + jj) + 2 * fc;
-                if (jg + jj < WN && lc < 2 * nb) {
-                  const double k0 = -acc[i][j][0], k1 = -acc[i][j][1];
-                  if (s == 1) {
-                    R1[i][j][0] = k0; R1[i][j][1] = k1;
-                    R2[i][j][0] = 0.0; R2[i][j][1] = 0.0;
-                    u[jj].x += h2 * v[jj].x * ima;
-                    u[jj].y += h2 * v[jj].y * ima;
-                  } else if (s == 2) {
-                    R2[i][j][0] = k0; R2[i][j][1] = k1;
-                    u[jj].x += hh4 * R1[i][j][0] * ima;
-                    u[jj].y += hh4 * R1[i][j][1] * ima;
-                  } else if (s == 3) {
-                    const double a1x = R1[i][j][0], a1y = R1[i][j][1], a2x = R2[i][j][0], a2y = R2[i][j][1];
-                    u[jj].x += (h2 * v[jj].x + hh2 * a2x - hh4 * a1x) * ima;
-                    u[jj].y += (h2 * v[jj].y + hh2 * a2y - hh4 * a1y) * ima;
-                    R1[i][j][0] = hh6 * (a1x + a2x + k0) - hh2 * a2x;
-                    R1[i][j][1] = hh6 * (a1y + a2y + k1) - hh2 * a2y;
-                    R2[i][j][0] = a1x + 2.0 * a2x + 2.0 * k0;
-                    R2[i][j][1] = a1y + 2.0 * a2y + 2.0 * k1;
-                  } else {
-                    u[jj].x += R1[i][j][0] * ima;
-                    u[jj].y += R1[i][j][1] * ima;
-                    v[jj].x += h6 * (R2[i][j][0] + k0);
-                    v[jj].y += h6 * (R2[i][j][1] + k1);
-                    vrow[lc >> 1] = v[jj];
-                  }
-                  urow[(lc ^ sw) >> 1] = u[jj];
-                }
-              }
-            }
-          }
-        }
+        // ---- phase B: RK4 bookkeeping, next stage operand in place
+        if (s == 1) chunk_phase_b<1, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
+        else if (s == 2) chunk_phase_b<2, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
+        else if (s == 3) chunk_phase_b<3, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
+        else chunk_phase_b<4, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
         if (t < d && s < 4) H[t * ldh + t] = hcur[s * dp + t];
         if (s == 4 && has_next) {
           double *hn = hdv + ((step + 1) & 1) * nhd;
@@ -368,6 +377,281 @@ k_rk4_chunk(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
       rec[E.qps + 2 * d * d + a * 2 * d + gcol] = V[a * ldu + lc];
     }
     PT(8);
+  }
+}
+
+// ------------------------------------------------------------------ warp-private column tiles -------------
+// Second formulation of the chunk kernel.  Warp j of the CTA owns tile j of the chunk: the 4 columns
+// b = b0 + 4j .. b0 + 4j + 3 of BOTH halves, interleaved as local columns (2 lb, 2 lb + 1) = (q-half, p-half), and ALL
+// rows.  Then
+//   * the B operand of H U_s (an 8-column slab of U_s) and the elements the warp updates in phase B are the same
+//     warp-private 60 x 8 slab: MMA and bookkeeping are separated by __syncwarp, never by a CTA barrier
+//   * each thread ends up with (Mqq, Mqp, Mpq, Mpp)[a][b] of its elements in registers after stage 4: the
+//     prefactor-matrix column is assembled without touching shared memory
+//   * the Hessian is held as H_s = H0 + diag(h_s): the dense base H0 (shared memory, zero off-diagonal part of the
+//     separable model, loaded once) is multiplied in full on the tensor pipe, the stage-dependent diagonal is
+//     added to the A fragment of the diagonal tile (one predicated add per k-step).  No per-stage rewrite of H, so
+//     the warps of a CTA drift freely inside a time step; ONE CTA barrier per step swaps the double-buffered
+//     Hessian diagonals.
+// Layout of a slab in shared memory: row-major [row][8]; B-fragment loads (4 rows x 8 columns = 256 contiguous
+// bytes) and the 128-bit owner accesses (8 rows x 64 bytes) are conflict free without swizzling.
+__host__ __device__ constexpr int cols_ldh(int nk);
+struct ColsLayout {
+  int nc, nb, ntile, ldh, dk;
+  int off_H, off_T, off_hd, off_c, slab, total;   // doubles
+};
+
+__host__ __device__ inline ColsLayout make_cols_layout(int d) {
+  ColsLayout L;
+  L.nc = (d <= 60) ? 3 : 4;
+  L.nb = (d + L.nc - 1) / L.nc;
+  L.ntile = (L.nb + 3) / 4;
+  L.dk = (d + 3) & ~3;
+  L.ldh = cols_ldh(L.dk / 4);
+  const int dp = (d + 1) & ~1;
+  int o = 0;
+  L.off_H = o; o += d * L.ldh;
+  L.slab = (L.dk + d) * 8;                 // U slab (dk rows, zero padded) + V slab (d rows)
+  L.off_T = o; o += L.ntile * L.slab;
+  L.off_hd = o; o += 2 * 4 * dp;
+  L.off_c = o; o += 4 * dp;
+  L.total = (o + 1) & ~1;
+  return L;
+}
+
+template <int S>
+__device__ __forceinline__ void cols_phase_b(double2 &u, double2 &v, double ima, double h, double k0, double k1, double (&R1)[2],
+                                             double (&R2)[2]) {
+  const double hh4 = 0.25 * h * h, hh2 = 0.5 * h * h, hh6 = h * h / 6.0, h2 = 0.5 * h, h6 = h / 6.0;
+  if (S == 1) {
+    R1[0] = k0; R1[1] = k1;
+    u.x = fma(h2 * ima, v.x, u.x);
+    u.y = fma(h2 * ima, v.y, u.y);
+  } else if (S == 2) {
+    R2[0] = k0; R2[1] = k1;
+    u.x = fma(hh4 * ima, R1[0], u.x);
+    u.y = fma(hh4 * ima, R1[1], u.y);
+  } else if (S == 3) {
+    const double a1x = R1[0], a1y = R1[1], a2x = R2[0], a2y = R2[1];
+    u.x += (h2 * v.x + hh2 * a2x - hh4 * a1x) * ima;
+    u.y += (h2 * v.y + hh2 * a2y - hh4 * a1y) * ima;
+    R1[0] = hh6 * (a1x + a2x + k0) - hh2 * a2x;
+    R1[1] = hh6 * (a1y + a2y + k1) - hh2 * a2y;
+    R2[0] = a1x + 2.0 * a2x + 2.0 * k0;
+    R2[1] = a1y + 2.0 * a2y + 2.0 * k1;
+  } else {
+    u.x = fma(R1[0], ima, u.x);
+    u.y = fma(R1[1], ima, u.y);
+    v.x = fma(h6, R2[0] + k0, v.x);
+    v.y = fma(h6, R2[1] + k1, v.y);
+  }
+}
+
+// leading dimension of the Hessian base for NK k-steps: >= 4 NK with ld mod 16 in {4, 12} (conflict-free A fragments)
+__host__ __device__ constexpr int cols_ldh(int nk) { return (4 * nk) % 16 == 4 || (4 * nk) % 16 == 12 ? 4 * nk : ((4 * nk + 4) % 16 == 4 || (4 * nk + 4) % 16 == 12 ? 4 * nk + 4 : 4 * nk + 8); }
+
+// NK = number of k-steps (dk / 4): compile time, so that every fragment load has an immediate offset and the
+// diagonal tile of each k-step is static.  The stage loop is NOT unrolled (one copy of the MMA code).
+template <int NK>
+__global__ void __launch_bounds__(160, 3)
+k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
+           const double *__restrict__ hd, ColsLayout L) {
+  constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
+  constexpr int LDH = cols_ldh(NK), DK = 4 * NK;
+  extern __shared__ __align__(16) double smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nthr = blockDim.x;
+  const int d = E.d, nb = L.nb, nc = L.nc, dp = (d + 1) & ~1;
+  double *__restrict__ Us = smem + L.off_T + warp * L.slab;
+  double *__restrict__ Vs = Us + DK * 8;
+  double *hdv = smem + L.off_hd;                      // [2][4][dp]
+  const double *csa = smem + L.off_c, *cisa = csa + dp, *csb = cisa + dp, *cisb = csb + dp;
+  const int fr = lane >> 2, fc = lane & 3;
+  const bool pe = (fr == fc), po = (fr == fc + 4);    // lanes holding a diagonal element in even / odd k-steps
+  const bool last_ok = (8 * (MT - 1) + fr) < d;       // only the last row tile can stick out of the matrix
+  const double *__restrict__ Hfr = smem + L.off_H + (last_ok ? fr : 0) * LDH + fc;   // rows 8 i + fr (clamped in the last tile)
+  const double *__restrict__ Hfr0 = smem + L.off_H + fr * LDH + fc;
+  const double *__restrict__ Ub = Us + fc * 8 + fr;
+  double2 *__restrict__ Uo = reinterpret_cast<double2 *>(Us + fr * 8 + 2 * fc);
+  double2 *__restrict__ Vo = reinterpret_cast<double2 *>(Vs + fr * 8 + 2 * fc);
+  double ima[MT];
+#pragma unroll
+  for (int i = 0; i < MT; ++i) ima[i] = (8 * i + fr < d) ? P.imass[8 * i + fr] : 0.0;
+
+  // dense base of the Hessian: off-diagonal part (identically zero for the separable models served here)
+  for (int i = t; i < d * LDH; i += nthr) smem[L.off_H + i] = 0.0;
+  if (t < d) {
+    double *c = smem + L.off_c;
+    c[t] = 0.5 * E.sgt[t];
+    c[dp + t] = 0.5 * E.isgt[t];
+    c[2 * dp + t] = E.sgi[t];
+    c[3 * dp + t] = E.isgi[t];
+  }
+  const int nitems = ntb * nc;
+  const int nhd = 4 * dp;
+  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int tl = item / nc, chunk = item - tl * nc;
+    const int traj = traj0 + tl;
+    const int b0 = chunk * nb;
+    const int bend = (b0 + nb < d) ? b0 + nb : d;
+    const int b = b0 + 4 * warp + fc;                       // the column b this thread's elements belong to
+    const bool bok = b < bend;
+    double *rec = E.rec + (size_t)traj * E.rs;
+    __syncthreads();                                        // everybody is done with the previous item
+    for (int i = t; i < nhd; i += nthr) hdv[i] = hd[(size_t)tl * nhd + i];
+    // ---- load the slab: row a = 8 i + fr, element pair (2 fc, 2 fc + 1) = (q-half, p-half) of column b
+    {
+      double2 u[MT], v[MT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int a = 8 * i + fr;
+        u[i] = v[i] = make_double2(0.0, 0.0);
+        if (a < d && bok) {
+          const double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
+          u[i] = make_double2(ru[b], ru[d + b]);
+          v[i] = make_double2(rv[b], rv[d + b]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int a = 8 * i + fr;
+        if (a < DK) Uo[i * 32] = u[i];
+        if (a < d) Vo[i * 32] = v[i];
+      }
+    }
+    __syncthreads();
+
+    for (int step = 0; step < nsteps; ++step) {
+      const double *hcur = hdv + (step & 1) * nhd;
+      double pre[2] = {0.0, 0.0};
+      const bool has_next = step + 1 < nsteps;
+      if (has_next) {
+        const double *src = hd + ((size_t)(step + 1) * ntb + tl) * nhd;
+        if (t < nhd) pre[0] = src[t];
+        if (t + nthr < nhd) pre[1] = src[t + nthr];
+      }
+      double R1[MT][2], R2[MT][2];
+      double2 *out = cm + ((size_t)step * ntb + tl) * d * d + (size_t)fr * d + (bok ? b : 0);
+      const double sb = bok ? csb[b] : 0.0, isb = bok ? cisb[b] : 0.0;
+#pragma unroll 1
+      for (int s = 1; s <= 4; ++s) {
+        const double *__restrict__ hsf = hcur + (s - 1) * dp + fr;
+        // ---- H_s U_s on the tensor pipe: 8-row tiles x this warp's 8 columns
+        double acc[MT][2];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const double bf = Ub[kk * 32];
+          double af[MT];
+#pragma unroll
+          for (int i = 0; i < MT - 1; ++i) af[i] = Hfr0[i * 8 * LDH + 4 * kk];
+          af[MT - 1] = last_ok ? Hfr[(MT - 1) * 8 * LDH + 4 * kk] : 0.0;
+          {
+            const int id = kk >> 1;                          // tile that contains the diagonal of this k-step
+            const bool on = ((kk & 1) ? po : pe) && (id < MT - 1 || last_ok);
+            const double hv = hsf[(8 * id < 8 * (MT - 1) || last_ok) ? 8 * id : 0];
+            if (on) af[id] += hv;
+          }
+#pragma unroll
+          for (int i = 0; i < MT; ++i) dmma884(acc[i][0], acc[i][1], af[i], bf);
+        }
+        __syncwarp();
+        // ---- RK4 bookkeeping on the warp's own slab, stage operand in place
+        if (s == 1) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (i < MT - 1 || last_ok) {
+              double2 u = Uo[i * 32], v = Vo[i * 32];
+              cols_phase_b<1>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
+              Uo[i * 32] = u;
+            }
+        } else if (s == 2) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (i < MT - 1 || last_ok) {
+              double2 u = Uo[i * 32], v = make_double2(0.0, 0.0);
+              cols_phase_b<2>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
+              Uo[i * 32] = u;
+            }
+        } else if (s == 3) {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (i < MT - 1 || last_ok) {
+              double2 u = Uo[i * 32], v = Vo[i * 32];
+              cols_phase_b<3>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
+              Uo[i * 32] = u;
+            }
+        } else {
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (i < MT - 1 || last_ok) {
+              double2 u = Uo[i * 32], v = Vo[i * 32];
+              cols_phase_b<4>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
+              Uo[i * 32] = u;
+              Vo[i * 32] = v;
+              // prefactor-matrix element (propagators.py:969-986, diagonal width matrices) straight from registers:
+              // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
+              if (bok) {
+                const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
+                out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
+              }
+            }
+        }
+        __syncwarp();
+      }
+      // ---- Hessian diagonals of the next step into the other buffer; one CTA barrier per time step
+      if (has_next) {
+        double *hn = hdv + ((step + 1) & 1) * nhd;
+        if (t < nhd) hn[t] = pre[0];
+        if (t + nthr < nhd) hn[t + nthr] = pre[1];
+      }
+      __syncthreads();
+    }
+    // ---- write back
+    if (bok) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int a = 8 * i + fr;
+        if (a < d) {
+          const double2 u = Uo[i * 32], v = Vo[i * 32];
+          double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
+          ru[b] = u.x; ru[d + b] = u.y;
+          rv[b] = v.x; rv[d + b] = v.y;
+        }
+      }
+    }
+  }
+}
+
+static bool cols_supported(const EngDev &E, const PotDev &P) {
+  if (!E.diag || E.dr != E.d) return false;
+  if (P.type != POT_MORSE && P.type != POT_NONHARMONIC) return false;
+  if (E.d <= 32 || E.d > 64) return false;
+  const ColsLayout L = make_cols_layout(E.d);
+  return L.ntile <= 5;
+}
+
+template <int NK>
+static cudaError_t launch_cols_t(int grid, int threads, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps,
+                                 int traj0, int ntb, double2 *cm, const double *hd, const ColsLayout &L, cudaStream_t st) {
+  cudaError_t ce = cudaFuncSetAttribute(k_rk4_cols<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return ce;
+  k_rk4_cols<NK><<<grid, threads, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_cols(int grid, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb, double2 *cm,
+                               const double *hd, const ColsLayout &L, cudaStream_t st) {
+  const size_t smem = sizeof(double) * (size_t)L.total;
+  const int threads = 32 * L.ntile;
+  switch (L.dk / 4) {
+#define SC_COLS_CASE(N) case N: return launch_cols_t<N>(grid, threads, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st);
+    SC_COLS_CASE(9) SC_COLS_CASE(10) SC_COLS_CASE(11) SC_COLS_CASE(12) SC_COLS_CASE(13) SC_COLS_CASE(14) SC_COLS_CASE(15)
+    SC_COLS_CASE(16)
+#undef SC_COLS_CASE
+    default: return cudaErrorInvalidValue;
   }
 }
 

@@ -533,6 +533,8 @@ static int ensure_partials(sc_engine *e, size_t need, cudaStream_t st) {
 static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
   const int d = e->dev.d, n = e->dev.n, sm = e->sm_count;
   const ChunkLayout L = make_chunk_layout(d);
+  const ColsLayout LC = make_cols_layout(d);
+  const bool use_cols = cols_supported(e->dev, P) && !getenv("SC_NO_COLS");
   const size_t smem = sizeof(double) * (size_t)L.total;
   int KC = 8;
   if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
@@ -550,8 +552,11 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
     CU(cudaStreamSynchronize(st));
     if (e->chunk_scratch) cudaFree(e->chunk_scratch);
     e->chunk_scratch = nullptr;
-    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
-    e->chunk_scratch_cap = need_bytes;
+    // sized for the largest step count per launch so that a later call with another K does not reallocate
+    const size_t per16 = per_traj / KC * 16;
+    size_t want = std::max(need_bytes, std::min(budget, per16 * (size_t)n));
+    CU(cudaMalloc(&e->chunk_scratch, want));
+    e->chunk_scratch_cap = want;
   }
   double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
   double2 *det = cm + (size_t)KC * ntb * d * d;
@@ -567,11 +572,17 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
     for (long long t0 = 0; t0 < n; t0 += ntb) {
       const int nt = (int)std::min<long long>(ntb, n - t0);
       long long grid = (long long)nt * L.nc;
-      if (grid > 3LL * sm) grid = 3LL * sm;
+      long long per_sm = 3;
+      if (const char *s2 = getenv("SC_CHUNK_CTAS")) per_sm = atoi(s2) > 0 ? atoi(s2) : 3;
+      if (grid > per_sm * sm) grid = per_sm * sm;
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
-      k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
-      CU(cudaGetLastError());
+      if (use_cols) {
+        CU(launch_cols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LC, st));
+      } else {
+        k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
+        CU(cudaGetLastError());
+      }
       CU(launch_lu_batch(cm, d, ks * nt, det, sm, st));
       const int nblk = (nt + 127) / 128;
       k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
@@ -583,7 +594,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
   e->launches += 1;
-  e->kernel_name = "k_rk4_chunk+k_lu_left+k_hk_finish";
+  e->kernel_name = use_cols ? "k_rk4_cols+k_lu_left+k_hk_finish" : "k_rk4_chunk+k_lu_left+k_hk_finish";
   return SC_OK;
 }
 

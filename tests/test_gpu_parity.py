@@ -271,7 +271,7 @@ def test_chunked_path_against_oracle(d, cuda_device):
     pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
     a0, i0 = pr.autocorrelation(m.en_zpt), pr.ic_correlation(pot, m.en_zpt)
     a, i = pr.propagate(pot, dt, nt - 1, m.en_zpt)
-    assert pr.kernel_name().startswith("k_rk4_chunk")
+    assert pr.kernel_name().startswith("k_rk4_")
     assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
     assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
     # one more step through the drop-in API, then state / prefactor / branch signs of all trajectories
