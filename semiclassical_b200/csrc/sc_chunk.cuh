@@ -403,9 +403,11 @@ struct ColsLayout {
 
 __host__ __device__ inline ColsLayout make_cols_layout(int d) {
   ColsLayout L;
-  L.nc = (d <= 60) ? 3 : 4;
-  L.nb = (d + L.nc - 1) / L.nc;
-  L.ntile = (L.nb + 3) / 4;
+  // 4 warps per CTA (one per SM sub-partition: warps are bound to schedulers by warp index mod 4, so any other
+  // count leaves the FP64 pipes of the sub-partitions unevenly loaded), 4 columns b per warp
+  L.nb = 16;
+  L.nc = (d + L.nb - 1) / L.nb;
+  L.ntile = 4;
   L.dk = (d + 3) & ~3;
   L.ldh = cols_ldh(L.dk / 4);
   const int dp = (d + 1) & ~1;
@@ -453,7 +455,7 @@ __host__ __device__ constexpr int cols_ldh(int nk) { return (4 * nk) % 16 == 4 |
 // NK = number of k-steps (dk / 4): compile time, so that every fragment load has an immediate offset and the
 // diagonal tile of each k-step is static.  The stage loop is NOT unrolled (one copy of the MMA code).
 template <int NK>
-__global__ void __launch_bounds__(160, 3)
+__global__ void __launch_bounds__(128, 3)
 k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
            const double *__restrict__ hd, ColsLayout L) {
   constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
@@ -495,6 +497,7 @@ k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2
     const int bend = (b0 + nb < d) ? b0 + nb : d;
     const int b = b0 + 4 * warp + fc;                       // the column b this thread's elements belong to
     const bool bok = b < bend;
+    const bool tile_ok = b0 + 4 * warp < bend;              // warp uniform: this warp's tile holds at least one column
     double *rec = E.rec + (size_t)traj * E.rs;
     __syncthreads();                                        // everybody is done with the previous item
     for (int i = t; i < nhd; i += nthr) hdv[i] = hd[(size_t)tl * nhd + i];
@@ -533,7 +536,7 @@ k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2
       double2 *out = cm + ((size_t)step * ntb + tl) * d * d + (size_t)fr * d + (bok ? b : 0);
       const double sb = bok ? csb[b] : 0.0, isb = bok ? cisb[b] : 0.0;
 #pragma unroll 1
-      for (int s = 1; s <= 4; ++s) {
+      for (int s = 1; s <= (tile_ok ? 4 : 0); ++s) {
         const double *__restrict__ hsf = hcur + (s - 1) * dp + fr;
         // ---- H_s U_s on the tensor pipe: 8-row tiles x this warp's 8 columns
         double acc[MT][2];
