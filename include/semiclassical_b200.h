@@ -153,6 +153,11 @@ int sc_engine_get_prefactor(sc_engine *eng, double *c_dev /* c128 (n) sqrt(det),
 int sc_engine_num_trajectories(const sc_engine *eng);
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
 long long sc_engine_launch_count(const sc_engine *eng);
+/* per-kernel device time of the column-chunked path (CUDA events on the launching stream): enable, run
+ * sc_engine_step*, then read the accumulated milliseconds of { (q,p) path kernel, RK4/monodromy kernel, batched LU,
+ * branch tracking + contributions } -- bench.py's roofline figure of the dominant kernel */
+int sc_engine_set_timing(sc_engine *eng, int on);
+int sc_engine_get_timing(sc_engine *eng, double *ms4_host);
 /* name of the fused kernel variant the last sc_engine_step dispatched to (diagnostics) */
 const char *sc_engine_kernel_name(const sc_engine *eng);
 

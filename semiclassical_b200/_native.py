@@ -91,6 +91,8 @@ _SIGNATURES = {
     "sc_engine_num_trajectories": (ctypes.c_int, [_vp]),
     "sc_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "sc_engine_kernel_name": (ctypes.c_char_p, [_vp]),
+    "sc_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
+    "sc_engine_get_timing": (ctypes.c_int, [_vp, _vp]),
 }
 
 

@@ -101,6 +101,11 @@ struct sc_engine {
   size_t partials_cap = 0;
   void *chunk_scratch = nullptr;   // prefactor matrices, determinants, aux rows of one batch (chunked path)
   size_t chunk_scratch_cap = 0;
+  // optional per-kernel timing of the chunked path (CUDA events on the launching stream)
+  bool timing = false;
+  std::vector<cudaEvent_t> tev;
+  size_t tev_used = 0;
+  double tms[4] = {0.0, 0.0, 0.0, 0.0};   // k_qp_path, k_rk4_*, k_lu_*, k_hk_finish
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
   long long ntraj_norm = 0;
@@ -114,6 +119,7 @@ struct sc_engine {
     if (partials) cudaFree(partials);
     if (corr_dev) cudaFree(corr_dev);
     if (chunk_scratch) cudaFree(chunk_scratch);
+    for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
 };
 
@@ -575,18 +581,32 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       long long per_sm = 3;
       if (const char *s2 = getenv("SC_CHUNK_CTAS")) per_sm = atoi(s2) > 0 ? atoi(s2) : 3;
       if (grid > per_sm * sm) grid = per_sm * sm;
+      auto mark = [&]() {
+        if (!e->timing) return;
+        if (e->tev_used == e->tev.size()) {
+          cudaEvent_t ev;
+          cudaEventCreate(&ev);
+          e->tev.push_back(ev);
+        }
+        cudaEventRecord(e->tev[e->tev_used++], st);
+      };
+      mark();
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
+      mark();
       if (use_cols) {
         CU(launch_cols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LC, st));
       } else {
         k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
         CU(cudaGetLastError());
       }
+      mark();
       CU(launch_lu_batch(cm, d, ks * nt, det, sm, st));
+      mark();
       const int nblk = (nt + 127) / 128;
       k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
       CU(cudaGetLastError());
+      mark();
       g0 += nblk;
       e->launches += 4;
     }
@@ -695,7 +715,18 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   PotDev none = PotDev();
   none.d = d;
   none.imass = D.q0;  // never dereferenced beyond d entries in MODE_INIT
-  if (int rc = run_hk_kernel(e, none, 0.0, 0, MODE_INIT, nullptr, st)) return rc;
+  // at t = 0 every trajectory has Mqq = Mpp = 1, Mqp = Mpq = 0: the prefactor matrix (propagators.py:969-994) and its
+  // determinant are the same for the whole ensemble -> one LU, then broadcast (bit-identical to n separate LUs)
+  {
+    const int n_all = D.n;
+    D.n = 1;
+    const int rc = run_hk_kernel(e, none, 0.0, 0, MODE_INIT, nullptr, st);
+    D.n = n_all;
+    if (rc) return rc;
+    k_broadcast_prefactor<<<(n_all + 255) / 256, 256, 0, st>>>(D.c2, D.c, D.sign, n_all);
+    CU(cudaGetLastError());
+    e->launches += 1;
+  }
   if (e->cfg.wm) {
     if (int rc = wm_alloc(e->wm, e->ens, D, D.q0, D.p0, probi, e->sm_count, st)) return rc;
     if (int rc = wm_launch(e->wm, e->dev, WM_INIT, 0.0, nullptr, nullptr, st)) return rc;
@@ -827,6 +858,33 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
       CU(cudaStreamSynchronize(st));
     }
   }
+  return SC_OK;
+}
+
+// per-kernel timing of the chunked path: enable, run sc_engine_step*, then read the accumulated milliseconds
+extern "C" int sc_engine_set_timing(sc_engine *e, int on) {
+  if (!e) return fail(SC_ERR_INVALID, "null engine");
+  e->timing = on != 0;
+  e->tev_used = 0;
+  for (double &x : e->tms) x = 0.0;
+  return SC_OK;
+}
+
+extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
+  if (!e || !ms4) return fail(SC_ERR_INVALID, "null argument");
+  if (e->tev_used) {
+    CU(cudaEventSynchronize(e->tev[e->tev_used - 1]));
+    for (size_t i = 0; i + 4 < e->tev_used + 1 && i + 4 < e->tev.size() + 1; i += 5) {
+      if (i + 4 >= e->tev_used) break;
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e->tev[i + k], e->tev[i + k + 1]));
+        e->tms[k] += ms;
+      }
+    }
+    e->tev_used = 0;
+  }
+  for (int k = 0; k < 4; ++k) ms4[k] = e->tms[k];
   return SC_OK;
 }
 

@@ -297,6 +297,16 @@ __global__ void k_init_records(EngDev E, const double *zi, const double *probi, 
   }
 }
 
+// prefactor of trajectory 0 -> all trajectories (initial conditions: identical monodromy matrices)
+__global__ void k_broadcast_prefactor(double2 *c2, double2 *c, double *sign, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 0 && i < n) {
+    c2[i] = c2[0];
+    c[i] = c[0];
+    sign[i] = sign[0];
+  }
+}
+
 // layout conversion: records <-> the reference's y (2d+4d^2+1, n)
 __global__ void k_export_state(EngDev E, double *y, int to_y) {
   const int d = E.d, n = E.n, d2 = d * d, L = 2 * d + 4 * d2 + 1;
