@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--no-mma", action="store_true", help="force the DFMA kernel (diagnostics)")
     args = ap.parse_args()
 
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL would print its version banner on stdout next to the JSON line
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
