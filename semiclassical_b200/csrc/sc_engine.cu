@@ -102,6 +102,8 @@ struct sc_engine {
   void *chunk_scratch = nullptr;   // prefactor matrices, determinants, aux rows of one batch (chunked path)
   size_t chunk_scratch_cap = 0;
   // optional per-kernel timing of the chunked path (CUDA events on the launching stream)
+  cudaStream_t s2 = nullptr;       // second stream of the chunked pipeline (LU / finish side)
+  cudaEvent_t ev_rk4[2] = {nullptr, nullptr}, ev_lu[2] = {nullptr, nullptr}, ev_join = nullptr;
   bool timing = false;
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -120,6 +122,12 @@ struct sc_engine {
     if (corr_dev) cudaFree(corr_dev);
     if (chunk_scratch) cudaFree(chunk_scratch);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_rk4[i]) cudaEventDestroy(ev_rk4[i]);
+      if (ev_lu[i]) cudaEventDestroy(ev_lu[i]);
+    }
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (s2) cudaStreamDestroy(s2);
   }
 };
 
@@ -545,71 +553,108 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   int KC = 8;
   if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
   if (KC > nsteps) KC = nsteps;
+  // Two-stream software pipeline: the RK4 kernel of batch i+1 (FP64 tensor pipe bound) runs concurrently with the LU
+  // kernel of batch i (latency / issue bound) on the SAME SMs -- 2 RK4 CTAs + 1 LU CTA fit in the shared memory and
+  // the register file of an SM -- with double-buffered scratch.  SC_CHUNK_OVERLAP=0 serialises the kernels.
+  bool overlap = false;
+  if (const char *s = getenv("SC_CHUNK_OVERLAP")) overlap = atoi(s) != 0;
+  const int nbuf = overlap ? 2 : 1;
   const int dp = (d + 1) & ~1;
   const size_t per_traj = (size_t)KC * ((size_t)d * d * sizeof(double2) + sizeof(double2) + 8 * sizeof(double) + 4 * dp * sizeof(double));
   size_t budget = (size_t)3 << 30;
   if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
-  long long ntb = (long long)(budget / per_traj);
+  long long ntb = (long long)(budget / nbuf / per_traj);
   ntb = (ntb / sm) * sm;
   if (ntb < sm) ntb = sm;
   if (ntb > n) ntb = n;
-  const size_t need_bytes = per_traj * (size_t)ntb;
+  const size_t buf_bytes = (per_traj * (size_t)ntb + 255) & ~(size_t)255;
+  const size_t need_bytes = buf_bytes * nbuf;
   if (need_bytes > e->chunk_scratch_cap) {
     CU(cudaStreamSynchronize(st));
     if (e->chunk_scratch) cudaFree(e->chunk_scratch);
     e->chunk_scratch = nullptr;
     // sized for the largest step count per launch so that a later call with another K does not reallocate
     const size_t per16 = per_traj / KC * 16;
-    size_t want = std::max(need_bytes, std::min(budget, per16 * (size_t)n));
+    size_t want = std::max(need_bytes, std::min(budget, per16 * (size_t)n * nbuf) + 512);
     CU(cudaMalloc(&e->chunk_scratch, want));
     e->chunk_scratch_cap = want;
   }
-  double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
-  double2 *det = cm + (size_t)KC * ntb * d * d;
-  double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
-  double *hd = aux + (size_t)KC * ntb * 8;
+  if (overlap && !e->s2) {
+    CU(cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU(cudaEventCreateWithFlags(&e->ev_rk4[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&e->ev_lu[i], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t s2 = overlap ? e->s2 : st;
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
   CU(cudaFuncSetAttribute(k_rk4_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  long long rk4_per_sm = 3, lu_per_sm = 0;   // 0: the LU launcher's default occupancy
+  if (const char *s = getenv("SC_CHUNK_CTAS")) rk4_per_sm = atoi(s) > 0 ? atoi(s) : rk4_per_sm;
+  if (const char *s = getenv("SC_LU_CTAS")) lu_per_sm = atoi(s) > 0 ? atoi(s) : lu_per_sm;
+  auto mark = [&](cudaStream_t stream) {
+    if (!e->timing) return;
+    if (e->tev_used == e->tev.size()) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      e->tev.push_back(ev);
+    }
+    cudaEventRecord(e->tev[e->tev_used++], stream);
+  };
+  if (overlap) {
+    // the second stream starts after everything already queued on the caller's stream
+    CU(cudaEventRecord(e->ev_join, st));
+    CU(cudaStreamWaitEvent(s2, e->ev_join, 0));
+  }
+  long long seq = 0;
   for (int s0 = 0; s0 < nsteps; s0 += KC) {
     const int ks = std::min(KC, nsteps - s0);
     size_t g0 = 0;
-    for (long long t0 = 0; t0 < n; t0 += ntb) {
+    for (long long t0 = 0; t0 < n; t0 += ntb, ++seq) {
       const int nt = (int)std::min<long long>(ntb, n - t0);
-      long long grid = (long long)nt * L.nc;
-      long long per_sm = 3;
-      if (const char *s2 = getenv("SC_CHUNK_CTAS")) per_sm = atoi(s2) > 0 ? atoi(s2) : 3;
-      if (grid > per_sm * sm) grid = per_sm * sm;
-      auto mark = [&]() {
-        if (!e->timing) return;
-        if (e->tev_used == e->tev.size()) {
-          cudaEvent_t ev;
-          cudaEventCreate(&ev);
-          e->tev.push_back(ev);
-        }
-        cudaEventRecord(e->tev[e->tev_used++], st);
-      };
-      mark();
+      const int buf = (int)(seq % nbuf);
+      unsigned char *base = reinterpret_cast<unsigned char *>(e->chunk_scratch) + buf_bytes * buf;
+      double2 *cm = reinterpret_cast<double2 *>(base);
+      double2 *det = cm + (size_t)KC * ntb * d * d;
+      double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
+      double *hd = aux + (size_t)KC * ntb * 8;
+      long long grid = (long long)nt * (use_cols ? LC.nc : L.nc);
+      if (grid > rk4_per_sm * sm) grid = rk4_per_sm * sm;
+      // producer side (caller's stream): this scratch buffer must have been consumed (two batches ago)
+      if (overlap && seq >= nbuf) CU(cudaStreamWaitEvent(st, e->ev_lu[buf], 0));
+      mark(st);
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
-      mark();
+      mark(st);
       if (use_cols) {
         CU(launch_cols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LC, st));
       } else {
         k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
         CU(cudaGetLastError());
       }
-      mark();
-      CU(launch_lu_batch(cm, d, ks * nt, det, sm, st));
-      mark();
+      mark(st);
+      // consumer side (second stream): determinants, branch tracking, contributions
+      if (overlap) {
+        CU(cudaEventRecord(e->ev_rk4[buf], st));
+        CU(cudaStreamWaitEvent(s2, e->ev_rk4[buf], 0));
+      }
+      mark(s2);
+      CU(launch_lu_batch(cm, d, ks * nt, det, sm, (int)lu_per_sm, s2));
+      mark(s2);
       const int nblk = (nt + 127) / 128;
-      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
+      k_hk_finish<<<nblk, 128, 0, s2>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
       CU(cudaGetLastError());
-      mark();
+      if (overlap) CU(cudaEventRecord(e->ev_lu[buf], s2));
       g0 += nblk;
       e->launches += 4;
     }
+  }
+  if (overlap) {
+    CU(cudaEventRecord(e->ev_join, s2));
+    CU(cudaStreamWaitEvent(st, e->ev_join, 0));
   }
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
@@ -874,13 +919,16 @@ extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
   if (!e || !ms4) return fail(SC_ERR_INVALID, "null argument");
   if (e->tev_used) {
     CU(cudaEventSynchronize(e->tev[e->tev_used - 1]));
-    for (size_t i = 0; i + 4 < e->tev_used + 1 && i + 4 < e->tev.size() + 1; i += 5) {
-      if (i + 4 >= e->tev_used) break;
-      for (int k = 0; k < 4; ++k) {
-        float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, e->tev[i + k], e->tev[i + k + 1]));
-        e->tms[k] += ms;
-      }
+    CU(cudaDeviceSynchronize());
+    // per batch: [before qp_path, after qp_path, after rk4] on the producer stream, [before lu, after lu] on the consumer
+    for (size_t i = 0; i + 4 < e->tev_used; i += 5) {
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]));
+      e->tms[0] += ms;
+      CU(cudaEventElapsedTime(&ms, e->tev[i + 1], e->tev[i + 2]));
+      e->tms[1] += ms;
+      CU(cudaEventElapsedTime(&ms, e->tev[i + 3], e->tev[i + 4]));
+      e->tms[2] += ms;
     }
     e->tev_used = 0;
   }

@@ -183,10 +183,10 @@ int main(int argc, char **argv) {
     cudaMalloc(&ddet, sizeof(double2) * nmat);
     cudaMemcpy(dA, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    launch_lu_batch(dA, dr, nmat, ddet, 148, 0);
+    launch_lu_batch(dA, dr, nmat, ddet, 148, 3, 0);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
-    launch_lu_batch(dA, dr, nmat, ddet, 148, 0);
+    launch_lu_batch(dA, dr, nmat, ddet, 148, 3, 0);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
