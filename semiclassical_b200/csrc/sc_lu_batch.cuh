@@ -3,6 +3,7 @@
 #include <cstdlib>
 
 #include "sc_lu.cuh"
+#include "sc_lu_mma.cuh"
 
 namespace sc {
 
@@ -77,6 +78,16 @@ k_lu_leftc(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restri
 static cudaError_t launch_lu_batch(const double2 *mats, int dr, int nmat, double2 *det_out, int sm_count, int ctas_per_sm,
                                    cudaStream_t st) {
   if (nmat <= 0) return cudaSuccess;
+  if (dr > 32 && !getenv("SC_LU_DFMA")) {
+    // trailing updates on the FP64 tensor pipe (sc_lu_mma.cuh); 3 matrices per SM (60 KB of panels each at dr = 60)
+    const size_t smem = lum_smem_bytes(dr);
+    cudaError_t ce = cudaFuncSetAttribute(k_lu_mma<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 3);
+    if (grid > nmat) grid = nmat;
+    k_lu_mma<4, 3><<<grid, 128, smem, st>>>(mats, dr, nmat, det_out);
+    return cudaGetLastError();
+  }
   if (dr > 32 && !getenv("SC_LU_NOCOMPACT")) {
     int occ = 5;
     if (const char *s2 = getenv("SC_LU_OCC")) occ = atoi(s2);

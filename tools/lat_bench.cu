@@ -2,7 +2,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k_lat(double* out, long long* cyc, double x0, int n) {
-  __shared__ double sm[1024];
+  __shared__ __align__(16) double sm[1024];
   __shared__ unsigned su[64];
   const int t = threadIdx.x;
   sm[t % 1024] = x0 + t; su[t % 64] = t;
@@ -53,18 +53,46 @@ __global__ void k_lat(double* out, long long* cyc, double x0, int n) {
   t0 = clock64();
   for (int i = 0; i < n; ++i) x = exp(-x * 1e-3);
   t1 = clock64(); if (t == 0) cyc[9] = (t1 - t0);
+  // 10: dependent DMMA chain (same accumulator)
+  {
+    double c0 = x, c1 = x * 0.5, a = 1e-3, b = 1e-3;
+    t0 = clock64();
+    for (int i = 0; i < n; ++i) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    t1 = clock64(); if (t == 0) cyc[10] = (t1 - t0);
+    x += c0 + c1;
+  }
+  // 11: 8 independent DMMA accumulators per iteration (single-warp issue rate)
+  {
+    double c[8][2]; for (int k = 0; k < 8; ++k) { c[k][0] = x + k; c[k][1] = x - k; }
+    double a = 1e-3, b = 1e-3;
+    t0 = clock64();
+    for (int i = 0; i < n; ++i) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+    }
+    t1 = clock64(); if (t == 0) cyc[11] = (t1 - t0) / 8;
+    for (int k = 0; k < 8; ++k) x += c[k][0] + c[k][1];
+  }
+  // 12: rcp.approx.ftz.f64 + 2 Newton steps, dependent
+  t0 = clock64();
+  for (int i = 0; i < n; ++i) { double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x + 0.5)); r = r * fma(-(x + 0.5), r, 2.0); r = r * fma(-(x + 0.5), r, 2.0); x = r; }
+  t1 = clock64(); if (t == 0) cyc[12] = (t1 - t0);
+  // 13: shfl 32-bit dependent
+  { int v = t; t0 = clock64(); for (int i = 0; i < n; ++i) v = __shfl_sync(0xffffffffu, v + 1, (v + i) & 31); t1 = clock64(); if (t == 0) cyc[13] = (t1 - t0); x += v; }
+  // 14: STS.128 -> __syncwarp -> LDS.128 round trip
+  { double2 *s2 = reinterpret_cast<double2 *>(sm); t0 = clock64(); for (int i = 0; i < n; ++i) { s2[(t + i) & 255] = make_double2(x, x); __syncwarp(); x += s2[(t + i + 5) & 255].x; __syncwarp(); } t1 = clock64(); if (t == 0) cyc[14] = (t1 - t0); }
   out[blockIdx.x * blockDim.x + t] = x;
 }
 int main() {
   double* out; long long* cyc; cudaMalloc(&out, 8 * 1024); cudaMalloc(&cyc, 8 * 16);
-  const char* names[] = {"DFMA dep", "DMUL/DADD dep", "1.0/x dep", "LDS.32 chase", "redux.max", "__syncthreads", "STS+BAR+LDS", "shfl double+add", "sqrt", "exp"};
+  const char* names[] = {"DFMA dep", "DMUL/DADD dep", "1.0/x dep", "LDS.32 chase", "redux.max", "__syncthreads", "STS+BAR+LDS", "shfl double+add", "sqrt", "exp", "DMMA dep", "DMMA indep x8 (per DMMA)", "rcp.approx+2NR", "shfl32 dep", "STS128+syncwarp+LDS128"};
   for (int threads : {32, 128, 384, 512}) {
     const int n = 1000;
     k_lat<<<1, threads>>>(out, cyc, 1.5, n);
     cudaDeviceSynchronize();
     long long h[16]; cudaMemcpy(h, cyc, 8 * 16, cudaMemcpyDeviceToHost);
     printf("threads=%d:", threads);
-    for (int i = 0; i < 10; ++i) printf("  %s=%.1f", names[i], h[i] / (double)n);
+    for (int i = 0; i < 15; ++i) printf("  %s=%.1f", names[i], h[i] / (double)n);
     printf("\n");
   }
   return 0;
