@@ -40,6 +40,7 @@ struct LuMmaFixed {
   unsigned long long bar[LU_MAX_PANELS];
   unsigned long long dmask[LU_MAX_PANELS];   // rows retired once panel K is done (padding rows included)
   unsigned tmask[LU_MAX_PANELS];             // bit T: all 8 rows of row tile T are retired after panel K
+  int inv[LU_MAX_PANELS];                    // inversions contributed by the pivots of panel K (permutation parity)
   int ready;
   int pad[3];
 };
@@ -47,9 +48,9 @@ constexpr int LUM_PANEL_ELEMS = 64 * 4;   // double2 per panel slot
 static inline size_t lum_smem_bytes(int dr) { return sizeof(LuMmaFixed) + (size_t)((dr + 3) / 4) * LUM_PANEL_ELEMS * sizeof(double2); }
 
 __device__ __forceinline__ void lum_dmma(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(c0), "+d"(c1)
+      : "d"(a), "d"(b));
 }
 
 __device__ __forceinline__ void lum_bar_init(LuMmaFixed *sh, int t) {
@@ -72,10 +73,12 @@ __device__ __forceinline__ void lum_cfms(double2 &a, double2 b, double2 c) {
 
 // in-warp factorisation of panel J in the rows <-> lanes layout (lane l: rows l and l + 32); publishes pivots and,
 // unless this is the last panel, W = L inv(L_KK) into WJ.  done: rows retired before this panel.
-__device__ __forceinline__ void lum_panel(double2 (&lo)[4], double2 (&hi)[4], int ncol, unsigned long long done, bool last,
-                                          LuMmaFixed *sh, int J, double2 *WJ, int lane) {
+__device__ __forceinline__ void lum_panel(double2 (&lo)[4], double2 (&hi)[4], int ncol, unsigned long long done,
+                                          unsigned long long real_rows, bool last, LuMmaFixed *sh, int J, double2 *WJ,
+                                          int lane) {
   double2 llo[4], lhi[4];
   int pp[4];
+  int inv = 0;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     llo[c] = lhi[c] = make_double2(0.0, 0.0);
@@ -96,6 +99,7 @@ __device__ __forceinline__ void lum_panel(double2 (&lo)[4], double2 (&hi)[4], in
       py = __shfl_sync(0xffffffffu, py, p & 31);
       ix = __shfl_sync(0xffffffffu, ix, p & 31);
       iy = __shfl_sync(0xffffffffu, iy, p & 31);
+      inv += __popcll(((done & real_rows) >> p) >> 1);           // earlier pivots in rows below this one
       done |= 1ull << p;
       double2 flo = make_double2(lo[c].x * ix - lo[c].y * iy, lo[c].x * iy + lo[c].y * ix);
       double2 fhi = make_double2(hi[c].x * ix - hi[c].y * iy, hi[c].x * iy + hi[c].y * ix);
@@ -115,6 +119,7 @@ __device__ __forceinline__ void lum_panel(double2 (&lo)[4], double2 (&hi)[4], in
       sh->pv[J][c] = make_double2(1.0, 0.0);
     }
   }
+  if (lane == 0) sh->inv[J] = inv;
   if (last) return;
   if (lane == 0) {
     unsigned long long f = done & (done >> 1);
@@ -150,10 +155,13 @@ __device__ __forceinline__ void lum_panel(double2 (&lo)[4], double2 (&hi)[4], in
 // state of the second half of the factorisation when the pivots stay near the diagonal: one row per lane, half the
 // instructions on the critical path.  HI: the live rows are lane + 32.
 template <bool HI>
-__device__ __forceinline__ void lum_panel1(double2 (&a)[4], int ncol, unsigned long long done, bool last, LuMmaFixed *sh, int J,
-                                           double2 *WJ, int lane) {
+__device__ __forceinline__ void lum_panel1(double2 (&a)[4], int ncol, unsigned long long done, unsigned long long real_rows,
+                                           bool last, LuMmaFixed *sh, int J, double2 *WJ, int lane) {
   const int row = lane + (HI ? 32 : 0);
   bool dead = (done >> row) & 1ull;
+  const unsigned real_half = static_cast<unsigned>(HI ? real_rows >> 32 : real_rows);
+  const int above = HI ? 0 : __popc(static_cast<unsigned>(real_rows >> 32));   // retired real rows of the other half below p
+  int inv = 0;
   double2 l[4];
   int pp[4];
 #pragma unroll
@@ -166,6 +174,7 @@ __device__ __forceinline__ void lum_panel1(double2 (&a)[4], int ncol, unsigned l
       const double rr = fast_rcp(m == 0.0 ? 1.0 : m);
       const unsigned kk = __reduce_max_sync(0xffffffffu, key);
       const int p = static_cast<int>(kk & 63u), src = p & 31;
+      inv += __popc(((__ballot_sync(0xffffffffu, dead) & real_half) >> src) >> 1) + above;
       double px = a[c].x, py = a[c].y;
       double ix = px * rr, iy = -py * rr;
       px = __shfl_sync(0xffffffffu, px, src);
@@ -191,6 +200,7 @@ __device__ __forceinline__ void lum_panel1(double2 (&a)[4], int ncol, unsigned l
       sh->pv[J][c] = make_double2(1.0, 0.0);
     }
   }
+  if (lane == 0) sh->inv[J] = inv;
   if (last) return;
   const unsigned live = __ballot_sync(0xffffffffu, !dead);
   if (lane == 0) {
@@ -226,10 +236,22 @@ __device__ __forceinline__ void lum_panel1(double2 (&a)[4], int ncol, unsigned l
   }
 }
 
+// block column J of A in the accumulator layout (zero padding); A == nullptr: nothing to load
+__device__ __forceinline__ void lum_load_block(const double2 *__restrict__ A, int ld, int dr, int J, int g, int j, double2 (&v)[8]) {
+  const int col = 4 * J + j;
+#pragma unroll
+  for (int T = 0; T < 8; ++T) {
+    const int r = 8 * T + g;
+    v[T] = make_double2(0.0, 0.0);
+    if (A != nullptr && col < dr && r < dr) v[T] = A[(size_t)col * ld + r];
+  }
+}
+
 // A: element (LU row r, LU column c) at A[c * ld + r]; 32 < dr <= 64.  W: nblocks panel slots.  Determinant on warp 0.
 template <int NW>
-__device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld, int dr, LuMmaFixed *sh, double2 *W, int base,
-                                           unsigned parity, int w, int lane) {
+__device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const double2 *__restrict__ Anext, double2 (&nxt)[8],
+                                           int ld, int dr, LuMmaFixed *sh, double2 *W, int base, unsigned parity, int w,
+                                           int lane) {
   const int nblocks = (dr + 3) >> 2;
   const int g = lane >> 2, j = lane & 3;
   const int swl = (lane & ~3) | (j ^ ((g >> 1) & 3));          // swizzled position of (row g of a tile, column j)
@@ -239,17 +261,11 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
   for (int J = w; J < nblocks; J += NW) {
     double2 *WJ = W + (size_t)J * LUM_PANEL_ELEMS;               // mirror of this block column until it is factored
     double acc[8][2];
-    {
-      const int col = 4 * J + j;
 #pragma unroll
-      for (int T = 0; T < 8; ++T) {
-        const int r = 8 * T + g;
-        double2 v = make_double2(0.0, 0.0);
-        if (col < dr && r < dr) v = A[(size_t)col * ld + r];
-        acc[T][0] = v.x;
-        acc[T][1] = v.y;
-        WJ[T * 32 + swl] = v;
-      }
+    for (int T = 0; T < 8; ++T) {                                // loaded while the previous block was being factored
+      acc[T][0] = nxt[T].x;
+      acc[T][1] = nxt[T].y;
+      WJ[T * 32 + swl] = nxt[T];
     }
     unsigned long long done = pad_rows;
     LUM_T0()
@@ -257,10 +273,17 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
     for (int K = 0; K < J; ++K) {
       if (known <= K) {
         known = flow_peek(&sh->ready) - base;
+#if defined(LUM_SPIN)
+        while (known <= K) {
+          if (LUM_SPIN > 0) __nanosleep(LUM_SPIN);
+          known = flow_peek(&sh->ready) - base;
+        }
+#else
         if (known <= K) {
           flow_bar_wait(&sh->bar[K], parity);
           known = K + 1;
         }
+#endif
       }
       LUM_T(0)
       const int pk = sh->p[K][j];
@@ -270,20 +293,37 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
       __syncwarp();                                              // ... and read before this update overwrites them
       const double b0 = part ? -x.y : -x.x, b1 = part ? -x.x : x.y;
       const double2 *Wk = W + (size_t)K * LUM_PANEL_ELEMS + swl;
+      // the two k-steps of a tile are dependent (26 cycles); issue all first k-steps, then all second ones
+      double2 wv[8];
 #pragma unroll
-      for (int T = 0; T < 8; ++T) {
-        if (!((full >> T) & 1u)) {                               // warp-uniform: some row of this tile is still active
-          const double2 wv = Wk[T * 32];
-          lum_dmma(acc[T][0], acc[T][1], wv.x, b0);
-          lum_dmma(acc[T][0], acc[T][1], wv.y, b1);
+      for (int T = 0; T < 8; ++T)
+        if (!((full >> T) & 1u)) wv[T] = Wk[T * 32];             // warp-uniform: some row of this tile is still active
+#ifndef LUM_SKIP_UPD
+#pragma unroll
+      for (int T = 0; T < 8; ++T)
+        if (!((full >> T) & 1u)) lum_dmma(acc[T][0], acc[T][1], wv[T].x, b0);
+#pragma unroll
+      for (int T = 0; T < 8; ++T)
+        if (!((full >> T) & 1u)) {
+          lum_dmma(acc[T][0], acc[T][1], wv[T].y, b1);
           WJ[T * 32 + swl] = make_double2(acc[T][0], acc[T][1]);
         }
-      }
+#endif
       LUM_T(1)
     }
     if (J > 0) done = sh->dmask[J - 1];
+    // next block of this warp (or its first block of the CTA's next matrix): the loads fly during the factorisation
+    {
+      const bool same = J + NW < nblocks;
+      lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
+    }
     // the mirror is the transpose into the rows <-> lanes layout: factor, publish
     __syncwarp();
+#ifdef LUM_SKIP_PANEL
+    if (lane < 4) { sh->p[J][lane] = 4 * J + lane; sh->pv[J][lane] = make_double2(1.0, 0.0); }
+    if (lane == 0) { sh->dmask[J] = pad_rows | ((J + 1 < 16) ? ((1ull << (4 * J + 4)) - 1ull) : ~0ull); sh->tmask[J] = (1u << ((J + 1) >> 1)) - 1u; }
+    LUM_T(2)
+#else
     {
       const int sw = (lane >> 1) & 3, ncol = min(4, dr - 4 * J);
       const bool last = J + 1 == nblocks;
@@ -292,12 +332,12 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
 #pragma unroll
         for (int c = 0; c < 4; ++c) hi[c] = WJ[(lane + 32) * 4 + (c ^ sw)];
         LUM_T(2)
-        lum_panel1<true>(hi, ncol, done, last, sh, J, WJ, lane);
+        lum_panel1<true>(hi, ncol, done, ~pad_rows, last, sh, J, WJ, lane);
       } else if (static_cast<unsigned>(done >> 32) == 0xffffffffu) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) lo[c] = WJ[lane * 4 + (c ^ sw)];
         LUM_T(2)
-        lum_panel1<false>(lo, ncol, done, last, sh, J, WJ, lane);
+        lum_panel1<false>(lo, ncol, done, ~pad_rows, last, sh, J, WJ, lane);
       } else {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -305,9 +345,10 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
           hi[c] = WJ[(lane + 32) * 4 + (c ^ sw)];
         }
         LUM_T(2)
-        lum_panel(lo, hi, min(4, dr - 4 * J), done, last, sh, J, WJ, lane);
+        lum_panel(lo, hi, min(4, dr - 4 * J), done, ~pad_rows, last, sh, J, WJ, lane);
       }
     }
+#endif
     LUM_T(3)
     __syncwarp();
     if (lane == 0) {
@@ -319,15 +360,11 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, int ld
   double2 det = make_double2(1.0, 0.0);
   if (w == 0) {
     flow_bar_wait(&sh->bar[nblocks - 1], parity);
-    int inv = 0;
+    int inv = lane < nblocks ? sh->inv[lane] : 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int k = lane + 32 * half;
-      if (k < dr) {
-        const int pk = sh->p[k >> 2][k & 3];
-        det = cmul(det, sh->pv[k >> 2][k & 3]);
-        for (int k2 = 0; k2 < k; ++k2) inv += (sh->p[k2 >> 2][k2 & 3] > pk) ? 1 : 0;
-      }
+      if (k < dr) det = cmul(det, sh->pv[k >> 2][k & 3]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -351,9 +388,13 @@ k_lu_mma(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restrict
   lum_bar_init(sh, t);
   int base = 0;
   unsigned parity = 0;
+  double2 nxt[8];
+  lum_load_block(blockIdx.x < nmat ? mats + (size_t)blockIdx.x * dr * dr : nullptr, dr, dr, w, lane >> 2, lane & 3, nxt);
   for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
     __syncthreads();   // panel slots and barriers of the previous matrix are no longer in use
-    const double2 det = lum_det<NW>(mats + (size_t)mat * dr * dr, dr, dr, sh, W, base, parity, w, lane);
+    const int matn = mat + gridDim.x;
+    const double2 det = lum_det<NW>(mats + (size_t)mat * dr * dr, matn < nmat ? mats + (size_t)matn * dr * dr : nullptr, nxt, dr,
+                                    dr, sh, W, base, parity, w, lane);
     base += nblocks;
     parity ^= 1u;
     if (t == 0) det_out[mat] = det;

@@ -5,7 +5,6 @@
 #include <cstdlib>
 #include <vector>
 #include <cuda_runtime.h>
-#define LUM_PROF
 #include "../semiclassical_b200/csrc/sc_lu_mma.cuh"
 #include "../semiclassical_b200/csrc/sc_lu_batch.cuh"
 using namespace sc;
@@ -32,6 +31,7 @@ template <int OCC> static float run_mma(const double2 *dA, int dr, int nmat, dou
   k_lu_mma<4, OCC><<<grid, 128, smem>>>(dA, dr, nmat, ddet);
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
+#ifdef LUM_PROF
   long long hp[4][8];
   cudaMemcpyFromSymbol(hp, lum_prof, sizeof(hp));
   const double nm = 2.0 * nmat;   // two launches, all CTAs accumulate
@@ -40,11 +40,13 @@ template <int OCC> static float run_mma(const double2 *dA, int dr, int nmat, dou
            hp[w][0] / nm, hp[w][1] / nm, hp[w][2] / nm, hp[w][3] / nm, hp[w][4] / nm);
   long long z[4][8] = {};
   cudaMemcpyToSymbol(lum_prof, z, sizeof(z));
+#endif
   return ms;
 }
 int main(int argc, char **argv) {
   const int nmat = argc > 1 ? atoi(argv[1]) : 148 * 48;
   const int only = argc > 2 ? atoi(argv[2]) : 0;
+  const int diag = argc > 3 ? atoi(argv[3]) : 0;   // 1: all matrices diagonal (the separable AS model)
   int drs[] = {60, 64, 33, 45, 51, 62, 37};
   for (int dr : drs) {
     if (only && dr != only) continue;
@@ -52,7 +54,7 @@ int main(int argc, char **argv) {
     srand(dr);
     for (int m = 0; m < nmat; ++m)
       for (int i = 0; i < dr * dr; ++i) {
-        const bool diag_only = (m % 4 == 2);
+        const bool diag_only = diag || (m % 4 == 2);
         const int r = i / dr, c = i % dr;
         cd v(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
         if (m % 4 == 3) v *= 0.05;                      // near-identity (the early-time prefactor matrices)
