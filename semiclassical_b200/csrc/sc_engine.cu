@@ -549,10 +549,17 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   const ChunkLayout L = make_chunk_layout(d);
   const ColsLayout LC = make_cols_layout(d);
   const bool use_cols = cols_supported(e->dev, P) && !getenv("SC_NO_COLS");
+  const WColsLayout LW = make_wcols_layout(d);
+  const bool use_wcols = use_cols && !getenv("SC_NO_WCOLS");
   const size_t smem = sizeof(double) * (size_t)L.total;
-  int KC = 8;
+  // time steps per pass over the state: the records are read and written once per pass, so longer passes amortise the
+  // state traffic and the pipeline fill (K = 8 -> 10 -> 20: +2.3 %, +4 %); passes of a launch are balanced
+  int KC = 20;
   if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
-  if (KC > nsteps) KC = nsteps;
+  {
+    const int npass = (nsteps + KC - 1) / KC;
+    KC = (nsteps + npass - 1) / npass;
+  }
   // Two-stream software pipeline: the RK4 kernel of batch i+1 (FP64 tensor pipe bound) runs concurrently with the LU
   // kernel of batch i (latency / issue bound) on the SAME SMs -- 2 RK4 CTAs + 1 LU CTA fit in the shared memory and
   // the register file of an SM -- with double-buffered scratch.  SC_CHUNK_OVERLAP=0 serialises the kernels.
@@ -574,8 +581,8 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
     if (e->chunk_scratch) cudaFree(e->chunk_scratch);
     e->chunk_scratch = nullptr;
     // sized for the largest step count per launch so that a later call with another K does not reallocate
-    const size_t per16 = per_traj / KC * 16;
-    size_t want = std::max(need_bytes, std::min(budget, per16 * (size_t)n * nbuf) + 512);
+    const size_t per20 = per_traj / KC * 20;
+    size_t want = std::max(need_bytes, std::min(budget, per20 * (size_t)n * nbuf) + 512);
     CU(cudaMalloc(&e->chunk_scratch, want));
     e->chunk_scratch_cap = want;
   }
@@ -622,6 +629,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
       double *hd = aux + (size_t)KC * ntb * 8;
       long long grid = (long long)nt * (use_cols ? LC.nc : L.nc);
+      if (use_wcols) grid = ((long long)nt * LW.nt + 3) / 4;
       if (grid > rk4_per_sm * sm) grid = rk4_per_sm * sm;
       // producer side (caller's stream): this scratch buffer must have been consumed (two batches ago)
       if (overlap && seq >= nbuf) CU(cudaStreamWaitEvent(st, e->ev_lu[buf], 0));
@@ -629,7 +637,9 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
       mark(st);
-      if (use_cols) {
+      if (use_wcols) {
+        CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, st));
+      } else if (use_cols) {
         CU(launch_cols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LC, st));
       } else {
         k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
@@ -647,6 +657,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       const int nblk = (nt + 127) / 128;
       k_hk_finish<<<nblk, 128, 0, s2>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
       CU(cudaGetLastError());
+      mark(s2);
       if (overlap) CU(cudaEventRecord(e->ev_lu[buf], s2));
       g0 += nblk;
       e->launches += 4;
@@ -659,7 +670,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
   e->launches += 1;
-  e->kernel_name = use_cols ? "k_rk4_cols+k_lu_left+k_hk_finish" : "k_rk4_chunk+k_lu_left+k_hk_finish";
+  e->kernel_name = use_wcols ? "k_rk4_wcols+k_lu_mma+k_hk_finish" : (use_cols ? "k_rk4_cols+k_lu_mma+k_hk_finish" : "k_rk4_chunk+k_lu_mma+k_hk_finish");
   return SC_OK;
 }
 
@@ -920,8 +931,8 @@ extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
   if (e->tev_used) {
     CU(cudaEventSynchronize(e->tev[e->tev_used - 1]));
     CU(cudaDeviceSynchronize());
-    // per batch: [before qp_path, after qp_path, after rk4] on the producer stream, [before lu, after lu] on the consumer
-    for (size_t i = 0; i + 4 < e->tev_used; i += 5) {
+    // per batch: [before qp_path, after qp_path, after rk4] on the producer stream, [before lu, after lu, after finish] on the consumer
+    for (size_t i = 0; i + 5 < e->tev_used; i += 6) {
       float ms = 0.0f;
       CU(cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]));
       e->tms[0] += ms;
@@ -929,6 +940,8 @@ extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
       e->tms[1] += ms;
       CU(cudaEventElapsedTime(&ms, e->tev[i + 3], e->tev[i + 4]));
       e->tms[2] += ms;
+      CU(cudaEventElapsedTime(&ms, e->tev[i + 4], e->tev[i + 5]));
+      e->tms[3] += ms;
     }
     e->tev_used = 0;
   }
