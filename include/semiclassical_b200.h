@@ -150,6 +150,15 @@ int sc_engine_set_state(sc_engine *eng, const double *y_dev, void *stream);
 int sc_engine_get_prefactor(sc_engine *eng, double *c_dev /* c128 (n) sqrt(det), principal branch */,
                             double *c2_dev /* c128 (n) det */, double *signs_dev /* (3, n): C, detA, detM */,
                             void *stream);
+/* ---- wavefunction diagnostics (Herman-Kluk): replace HermanKlukPropagator.coefficients / norm / wavefunction
+ *      (propagators.py:657-686, 734-782, 688-732).  norm(): A, B, C = Gi (Gi+Gj)^+ Gj, (Gi+Gj)^+, Gj (Gi+Gj)^+ and fac of
+ *      CoherentStatesOverlap(Gamma_t, Gamma_t) (propagators.py:174-179, 230), host (d x d) row-major; the result is the
+ *      complex double sum (its real part is |psi|^2).  wavefunction(): x_dev (d, nx), fac = (det Gt / pi^rank)^(1/4). */
+int sc_engine_coefficients(sc_engine *eng, double *v_dev /* c128 (n) */, void *stream);
+int sc_engine_norm(sc_engine *eng, const double *A_host, const double *B_host, const double *C_host, double fac,
+                   double *norm2_host /* [2] */, void *stream);
+int sc_engine_wavefunction(sc_engine *eng, const double *Gamma_t_host, double fac, int nx, const double *x_dev,
+                           double *phi_dev /* c128 (nx) */, void *stream);
 int sc_engine_num_trajectories(const sc_engine *eng);
 /* number of kernel launches issued by this engine so far (bench.py's gpu_launches) */
 long long sc_engine_launch_count(const sc_engine *eng);

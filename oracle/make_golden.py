@@ -187,6 +187,48 @@ def gdml_dynamics_case(name, propagators, potentials, gdml_predictor, ntraj, nt)
     _propagate(name, propagators, pot, fields, G0, G0, G0, pos, np.zeros(d), ntraj, dt, nt, en0)
 
 
+def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, dt, nt, en0, nx, seed=0, xspread=0.3):
+    """wavefunction diagnostics of the reference HK propagator after nt steps: coefficients(), norm(), wavefunction(x)
+    (propagators.py:657-782).  Stores q, p, S of every trajectory (not the monodromy blocks) besides the ensemble."""
+    torch.manual_seed(seed)
+    pr = propagators.HermanKlukPropagator(T(Gi), T(Gt))
+    pr.initial_conditions(T(q0), T(p0), T(G0), ntraj=ntraj)
+    zi, probi = pr.zi.numpy().copy(), pr.probi.numpy().copy()
+    auto, ic = refrun.run_reference(pr, potential, dt, nt, en0)
+    d = len(q0)
+    rng = np.random.default_rng(1000 + seed)
+    qm = pr.y.numpy()[:d].mean(axis=1)
+    x = qm[:, None] + xspread * rng.standard_normal((d, nx)) / np.sqrt(np.maximum(np.diag(Gt), 1e-3))[:, None]
+    out = dict(fields)
+    y = pr.y.numpy()
+    out.update(kind="HK", Gamma_i=Gi, Gamma_t=Gt, Gamma_0=G0, q0=q0, p0=p0, dt=dt, nt=nt, energy0_es=en0, zi=zi, probi=probi,
+               autocorrelation=auto, ic_correlation=ic, t_final=float(pr.t),
+               qpS_final=np.concatenate((y[:2 * d], y[-1:]), axis=0).copy(), c_final=pr.c.numpy().copy(),
+               signs_C=pr.sign_trackers["prefactorC"]["signs"].numpy().real.copy(),
+               coefficients=pr.coefficients().numpy().copy(), norm=float(pr.norm()), x=x,
+               wavefunction=np.asarray(pr.wavefunction(T(x))).copy())
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name:28s} n={ntraj:5d} nt={nt:4d} norm={out['norm']:.6f} max|psi|={np.abs(out['wavefunction']).max():.3e} "
+          f"{os.path.getsize(path)/1024:.0f} KB")
+
+
+def diag_morse(name, propagators, potentials, model, ntraj, nt, nx, rotate_seed=None, **kw):
+    dt, _ = workloads.test_time_grid()
+    pot = potentials.MorsePotential(T(model.omega.copy()), T(model.chi.copy()), T(model.nac.copy()))
+    G = np.diag(model.omega)
+    q0, p0 = model.q0, model.p0
+    fields = dict(potential="morse", omega=model.omega, chi=model.chi, nac=model.nac)
+    if rotate_seed is not None:
+        Q = workloads.random_orthogonal(model.dim, rotate_seed)
+        pot = refrun.RotatedPotential(pot, T(Q))
+        G = Q @ G @ Q.T
+        G = 0.5 * (G + G.T)
+        q0, p0 = Q @ q0, Q @ p0
+        fields.update(potential="rotated_morse", Q=Q)
+    diag_case(name, propagators, pot, fields, G, G, G, q0, p0, ntraj, dt, nt, model.en_zpt, nx, **kw)
+
+
 def main():
     prefixes = sys.argv[1:]
     os.makedirs(GOLDEN, exist_ok=True)
@@ -235,6 +277,20 @@ def main():
         # the fitted model itself is 500 KB: store only a hash-free recipe (shapes + outputs); the test rebuilds
         # nothing from it, it is a known-answer check for the oracle run inside this container only
         gdml_potential_case("gdml_pot_coumarin", gdml_predictor, model, xyz.reshape(-1), 2, seed=4, jitter=0.02)
+    if want("diag_as5"):
+        diag_morse("diag_as5", propagators, potentials, workloads.as_5modes(0.02), 300, 30, 40)
+    if want("diag_as5_rot"):
+        diag_morse("diag_as5_rot", propagators, potentials, workloads.as_5modes(0.02), 150, 20, 33, rotate_seed=7, seed=2)
+    if want("diag_as24"):
+        diag_morse("diag_as24", propagators, potentials, workloads.as_synthetic(24, seed=3), 130, 10, 70, seed=3)
+    if want("diag_1d"):
+        nt = 50
+        times = np.linspace(0.0, (12.0 / 40) * 2.0 * np.pi, 100)
+        pot = potentials.NonHarmonicPotential()
+        fields = dict(potential="nonharmonic", eps=np.array([0.975]), b=np.array([12.0 ** -0.5]))
+        Gi = np.array([[5.0]])
+        diag_case("diag_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 500,
+                  float(times[1] - times[0]), nt, 0.5, 128, seed=4, xspread=3.0)
     if want("hk_gdml4"):
         gdml_dynamics_case("hk_gdml4", propagators, potentials, gdml_predictor, 200, 40)
 

@@ -89,6 +89,9 @@ _SIGNATURES = {
     "sc_engine_set_state": (ctypes.c_int, [_vp, _vp, _vp]),
     "sc_engine_get_prefactor": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "sc_engine_num_trajectories": (ctypes.c_int, [_vp]),
+    "sc_engine_coefficients": (ctypes.c_int, [_vp, _vp, _vp]),
+    "sc_engine_norm": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp]),
+    "sc_engine_wavefunction": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, _vp]),
     "sc_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "sc_engine_kernel_name": (ctypes.c_char_p, [_vp]),
     "sc_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),

@@ -636,21 +636,24 @@ k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2
 // refilled by cp.async while the step is still running: stages 1-3 of step n + 1 when stage 4 of step n starts
 // (their region is dead by then), stage 4 right after the stage-4 MMA phase.
 struct WColsLayout {
-  int nt, ldh, dk;                                  // column tiles per trajectory
-  int off_H, off_c, off_W, wstride, off_hdw, total; // doubles; per-warp region: U slab, V slab, hd buffer
+  int nt, ntw, nitem, ldh, dk;                      // column tiles per trajectory, tiles per warp, warp items per trajectory
+  int off_H, off_c, off_W, slab, wstride, off_hdw, total; // doubles; per-warp region: ntw x (U slab, V slab), hd buffer
 };
-__host__ __device__ inline WColsLayout make_wcols_layout(int d) {
+__host__ __device__ inline WColsLayout make_wcols_layout(int d, int ntw) {
   WColsLayout L;
   L.nt = (d + 3) / 4;
+  L.ntw = ntw;
+  L.nitem = (L.nt + ntw - 1) / ntw;
   L.dk = (d + 3) & ~3;
   L.ldh = cols_ldh(L.dk / 4);
   const int dp = (d + 1) & ~1;
   int o = 0;
   L.off_H = o; o += d * L.ldh;
-  L.off_c = o; o += 4 * dp;
+  L.off_c = o; o += 6 * dp;                         // sa, isa, sb, isb, 1/m (+ zero padding up to 8 MT rows)
   o = (o + 1) & ~1;
   L.off_W = o;
-  L.off_hdw = (L.dk + d) * 8;
+  L.slab = (L.dk + d) * 8;
+  L.off_hdw = ntw * L.slab;
   L.wstride = L.off_hdw + 4 * dp;
   o += 4 * L.wstride;
   L.total = (o + 1) & ~1;
@@ -662,8 +665,11 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <int NK>
-__global__ void __launch_bounds__(128, 3)
+// NTW = column tiles per warp.  NTW = 2: every A fragment (Hessian) feeds two DMMAs -- the fragment loads were the
+// first stall of the one-tile kernel (shared-memory pipe 60 % busy) -- at the price of 2 x 48 accumulator / RK4
+// registers per thread, i.e. two CTAs per SM instead of three.
+template <int NK, int NTW>
+__global__ void __launch_bounds__(128, (NTW == 1 ? 3 : 2))
 k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
             const double *__restrict__ hd, WColsLayout L) {
   constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
@@ -671,65 +677,76 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nthr = blockDim.x;
   const int d = E.d, dp = (d + 1) & ~1;
-  double *__restrict__ Us = smem + L.off_W + warp * L.wstride;
-  double *__restrict__ Vs = Us + DK * 8;
-  double *__restrict__ hdw = Us + L.off_hdw;          // [4][dp], this warp's current time step
+  double *__restrict__ Wreg = smem + L.off_W + warp * L.wstride;
+  double *__restrict__ hdw = Wreg + L.off_hdw;        // [4][dp], this warp's current time step
   const double *csa = smem + L.off_c, *cisa = csa + dp, *csb = cisa + dp, *cisb = csb + dp;
   const int fr = lane >> 2, fc = lane & 3;
   const bool pe = (fr == fc), po = (fr == fc + 4);    // lanes holding a diagonal element in even / odd k-steps
   const bool last_ok = (8 * (MT - 1) + fr) < d;       // only the last row tile can stick out of the matrix
   const double *__restrict__ Hfr = smem + L.off_H + (last_ok ? fr : 0) * LDH + fc;
   const double *__restrict__ Hfr0 = smem + L.off_H + fr * LDH + fc;
-  const double *__restrict__ Ub = Us + fc * 8 + fr;
-  double2 *__restrict__ Uo = reinterpret_cast<double2 *>(Us + fr * 8 + 2 * fc);
-  double2 *__restrict__ Vo = reinterpret_cast<double2 *>(Vs + fr * 8 + 2 * fc);
-  double ima[MT];
+  const double *__restrict__ Ub = Wreg + fc * 8 + fr;                                       // + w * slab
+  double2 *__restrict__ Uo = reinterpret_cast<double2 *>(Wreg + fr * 8 + 2 * fc);           // + w * slab / 2
+  double2 *__restrict__ Vo = reinterpret_cast<double2 *>(Wreg + DK * 8 + fr * 8 + 2 * fc);
+  const int slab = L.slab, slab2 = L.slab / 2;
+  const double *cim = cisb + dp + fr;                   // 1 / m of row 8 i + fr at cim[8 i] (zero beyond d)
+  double ima[MT];                                       // NTW = 1 keeps them in registers (measured: 3.6 % faster)
 #pragma unroll
   for (int i = 0; i < MT; ++i) ima[i] = (8 * i + fr < d) ? P.imass[8 * i + fr] : 0.0;
 
   // dense base of the Hessian: off-diagonal part (identically zero for the separable models served here)
   for (int i = t; i < d * LDH; i += nthr) smem[L.off_H + i] = 0.0;
-  if (t < d) {
+  if (t < 2 * dp) {
     double *c = smem + L.off_c;
-    c[t] = 0.5 * E.sgt[t];
-    c[dp + t] = 0.5 * E.isgt[t];
-    c[2 * dp + t] = E.sgi[t];
-    c[3 * dp + t] = E.isgi[t];
+    if (t < d) {
+      c[t] = 0.5 * E.sgt[t];
+      c[dp + t] = 0.5 * E.isgt[t];
+      c[2 * dp + t] = E.sgi[t];
+      c[3 * dp + t] = E.isgi[t];
+    }
+    c[4 * dp + t] = t < d ? P.imass[t] : 0.0;
   }
   __syncthreads();                                      // the only CTA barrier
-  const int nt = L.nt;
-  const long long nitems = (long long)ntb * nt;
+  const int nt = L.nt, nitem = L.nitem;
+  const long long nitems = (long long)ntb * nitem;
   const int nhd = 4 * dp;
   const int c16_123 = 3 * dp / 2, c16_4 = dp / 2;       // 16-byte pieces of the stage 1-3 rows / of the stage-4 row
   for (long long item = (long long)blockIdx.x * 4 + warp; item < nitems; item += (long long)gridDim.x * 4) {
-    const int tl = static_cast<int>(item / nt), tile = static_cast<int>(item - (long long)tl * nt);
+    const int tl = static_cast<int>(item / nitem), it = static_cast<int>(item - (long long)tl * nitem);
     const int traj = traj0 + tl;
-    const int b = 4 * tile + fc;                            // the column b this thread's elements belong to
-    const bool bok = b < d;
+    int b[NTW];
+    bool bok[NTW];
+#pragma unroll
+    for (int w = 0; w < NTW; ++w) {
+      b[w] = 4 * (NTW * it + w) + fc;                       // the column b this thread's elements of tile w belong to
+      bok[w] = b[w] < d;
+    }
+    const bool two = NTW > 1 && (NTW * it + 1 < nt);        // warp-uniform: the second tile exists
     double *rec = E.rec + (size_t)traj * E.rs;
     __syncwarp();                                           // the previous item of this warp is finished
     {
       const double *src = hd + (size_t)tl * nhd;
       for (int i = lane; i < 2 * dp; i += 32) cp_async16(hdw + 2 * i, src + 2 * i);
     }
-    // ---- load the slab: row a = 8 i + fr, element pair (2 fc, 2 fc + 1) = (q-half, p-half) of column b
-    {
+    // ---- load the slabs: row a = 8 i + fr, element pair (2 fc, 2 fc + 1) = (q-half, p-half) of column b
+#pragma unroll
+    for (int w = 0; w < NTW; ++w) {
       double2 u[MT], v[MT];
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const int a = 8 * i + fr;
         u[i] = v[i] = make_double2(0.0, 0.0);
-        if (a < d && bok) {
+        if (a < d && bok[w]) {
           const double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
-          u[i] = make_double2(ru[b], ru[d + b]);
-          v[i] = make_double2(rv[b], rv[d + b]);
+          u[i] = make_double2(ru[b[w]], ru[d + b[w]]);
+          v[i] = make_double2(rv[b[w]], rv[d + b[w]]);
         }
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const int a = 8 * i + fr;
-        if (a < DK) Uo[i * 32] = u[i];
-        if (a < d) Vo[i * 32] = v[i];
+        if (a < DK) Uo[w * slab2 + i * 32] = u[i];
+        if (a < d) Vo[w * slab2 + i * 32] = v[i];
       }
     }
     cp_async_wait_all();
@@ -738,22 +755,25 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
     for (int step = 0; step < nsteps; ++step) {
       const bool has_next = step + 1 < nsteps;
       const double *hnext = hd + ((size_t)(step + 1) * ntb + tl) * nhd;
-      double R1[MT][2], R2[MT][2];
-      double2 *out = cm + ((size_t)step * ntb + tl) * d * d + (size_t)fr * d + (bok ? b : 0);
-      const double sb = bok ? csb[b] : 0.0, isb = bok ? cisb[b] : 0.0;
+      double R1[NTW][MT][2], R2[NTW][MT][2];
+      double2 *outb = cm + ((size_t)step * ntb + tl) * d * d + (size_t)fr * d;
 #pragma unroll 1
       for (int s = 1; s <= 4; ++s) {
         const double *__restrict__ hsf = hdw + (s - 1) * dp + fr;
         if (s == 4 && has_next) {                            // rows of stages 1-3 are dead: refill them for step + 1
           for (int i = lane; i < c16_123; i += 32) cp_async16(hdw + 2 * i, hnext + 2 * i);
         }
-        // ---- H_s U_s on the tensor pipe: 8-row tiles x this warp's 8 columns
-        double acc[MT][2];
+        // ---- H_s U_s on the tensor pipe: 8-row tiles x this warp's 8 (16) columns
+        double acc[NTW][MT][2];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = 0.0;
+        for (int w = 0; w < NTW; ++w)
+#pragma unroll
+          for (int i = 0; i < MT; ++i) acc[w][i][0] = acc[w][i][1] = 0.0;
 #pragma unroll
         for (int kk = 0; kk < NK; ++kk) {
-          const double bf = Ub[kk * 32];
+          double bf[NTW];
+#pragma unroll
+          for (int w = 0; w < NTW; ++w) bf[w] = Ub[w * slab + kk * 32];
           double af[MT];
 #pragma unroll
           for (int i = 0; i < MT - 1; ++i) af[i] = Hfr0[i * 8 * LDH + 4 * kk];
@@ -765,52 +785,63 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
             if (on) af[id] += hv;
           }
 #pragma unroll
-          for (int i = 0; i < MT; ++i) dmma884(acc[i][0], acc[i][1], af[i], bf);
+          for (int i = 0; i < MT; ++i) dmma884(acc[0][i][0], acc[0][i][1], af[i], bf[0]);
+          if (NTW > 1 && two) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) dmma884(acc[NTW - 1][i][0], acc[NTW - 1][i][1], af[i], bf[NTW - 1]);
+          }
         }
         __syncwarp();
-        // ---- RK4 bookkeeping on the warp's own slab, stage operand in place
-        if (s == 1) {
+        if (s == 4 && has_next) {                            // the stage-4 row has been consumed by the MMA phase
+          for (int i = lane; i < c16_4; i += 32) cp_async16(hdw + 3 * dp + 2 * i, hnext + 3 * dp + 2 * i);
+        }
+        // ---- RK4 bookkeeping on the warp's own slabs, stage operand in place
 #pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<1>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else if (s == 2) {
+        for (int w = 0; w < NTW; ++w) {
+          if (w > 0 && !two) break;
+          double2 *Uw = Uo + w * slab2, *Vw = Vo + w * slab2;
+          if (s == 1) {
 #pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = make_double2(0.0, 0.0);
-              cols_phase_b<2>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else if (s == 3) {
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<3>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else {
-          if (has_next) {                                    // the stage-4 row has been consumed by the MMA phase
-            for (int i = lane; i < c16_4; i += 32) cp_async16(hdw + 3 * dp + 2 * i, hnext + 3 * dp + 2 * i);
-          }
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<4>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-              Vo[i * 32] = v;
-              // prefactor-matrix element (propagators.py:969-986, diagonal width matrices) straight from registers:
-              // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
-              if (bok) {
-                const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
-                out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
+            for (int i = 0; i < MT; ++i)
+              if (i < MT - 1 || last_ok) {
+                double2 u = Uw[i * 32], v = Vw[i * 32];
+                cols_phase_b<1>(u, v, (NTW == 1 ? ima[i] : cim[8 * i]), h, -acc[w][i][0], -acc[w][i][1], R1[w][i], R2[w][i]);
+                Uw[i * 32] = u;
               }
-            }
+          } else if (s == 2) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+              if (i < MT - 1 || last_ok) {
+                double2 u = Uw[i * 32], v = make_double2(0.0, 0.0);
+                cols_phase_b<2>(u, v, (NTW == 1 ? ima[i] : cim[8 * i]), h, -acc[w][i][0], -acc[w][i][1], R1[w][i], R2[w][i]);
+                Uw[i * 32] = u;
+              }
+          } else if (s == 3) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+              if (i < MT - 1 || last_ok) {
+                double2 u = Uw[i * 32], v = Vw[i * 32];
+                cols_phase_b<3>(u, v, (NTW == 1 ? ima[i] : cim[8 * i]), h, -acc[w][i][0], -acc[w][i][1], R1[w][i], R2[w][i]);
+                Uw[i * 32] = u;
+              }
+          } else {
+            const double sb = bok[w] ? csb[b[w]] : 0.0, isb = bok[w] ? cisb[b[w]] : 0.0;
+            double2 *out = outb + (bok[w] ? b[w] : 0);
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+              if (i < MT - 1 || last_ok) {
+                double2 u = Uw[i * 32], v = Vw[i * 32];
+                cols_phase_b<4>(u, v, (NTW == 1 ? ima[i] : cim[8 * i]), h, -acc[w][i][0], -acc[w][i][1], R1[w][i], R2[w][i]);
+                Uw[i * 32] = u;
+                Vw[i * 32] = v;
+                // prefactor-matrix element (propagators.py:969-986, diagonal width matrices) straight from registers:
+                // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
+                if (bok[w]) {
+                  const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
+                  out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
+                }
+              }
+          }
         }
         __syncwarp();
       }
@@ -818,27 +849,30 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
       __syncwarp();
     }
     // ---- write back
-    if (bok) {
 #pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int a = 8 * i + fr;
-        if (a < d) {
-          const double2 u = Uo[i * 32], v = Vo[i * 32];
-          double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
-          ru[b] = u.x; ru[d + b] = u.y;
-          rv[b] = v.x; rv[d + b] = v.y;
+    for (int w = 0; w < NTW; ++w) {
+      if (bok[w]) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const int a = 8 * i + fr;
+          if (a < d) {
+            const double2 u = Uo[w * slab2 + i * 32], v = Vo[w * slab2 + i * 32];
+            double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
+            ru[b[w]] = u.x; ru[d + b[w]] = u.y;
+            rv[b[w]] = v.x; rv[d + b[w]] = v.y;
+          }
         }
       }
     }
   }
 }
 
-template <int NK>
+template <int NK, int NTW>
 static cudaError_t launch_wcols_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb,
                                   double2 *cm, const double *hd, const WColsLayout &L, cudaStream_t st) {
-  cudaError_t ce = cudaFuncSetAttribute(k_rk4_wcols<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t ce = cudaFuncSetAttribute(k_rk4_wcols<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  k_rk4_wcols<NK><<<grid, 128, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
+  k_rk4_wcols<NK, NTW><<<grid, 128, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
   return cudaGetLastError();
 }
 
@@ -846,7 +880,10 @@ static cudaError_t launch_wcols(int grid, const EngDev &E, const PotDev &P, doub
                                 const double *hd, const WColsLayout &L, cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)L.total;
   switch (L.dk / 4) {
-#define SC_WCOLS_CASE(N) case N: return launch_wcols_t<N>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st);
+#define SC_WCOLS_CASE(N)                                                                                              \
+  case N:                                                                                                             \
+    return L.ntw == 2 ? launch_wcols_t<N, 2>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st)                 \
+                      : launch_wcols_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st);
     SC_WCOLS_CASE(9) SC_WCOLS_CASE(10) SC_WCOLS_CASE(11) SC_WCOLS_CASE(12) SC_WCOLS_CASE(13) SC_WCOLS_CASE(14) SC_WCOLS_CASE(15)
     SC_WCOLS_CASE(16)
 #undef SC_WCOLS_CASE

@@ -18,6 +18,7 @@
 #include "sc_lu_batch.cuh"
 #include "sc_potentials.cuh"
 #include "sc_wm.cuh"
+#include "sc_gauss.cuh"
 
 using namespace sc;
 
@@ -549,7 +550,9 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   const ChunkLayout L = make_chunk_layout(d);
   const ColsLayout LC = make_cols_layout(d);
   const bool use_cols = cols_supported(e->dev, P) && !getenv("SC_NO_COLS");
-  const WColsLayout LW = make_wcols_layout(d);
+  int wcols_tiles = 1;                                  // column tiles per warp of k_rk4_wcols (2: measured slower, 8 warps / SM)
+  if (const char *s = getenv("SC_WCOLS_TILES")) wcols_tiles = atoi(s) == 2 ? 2 : 1;
+  const WColsLayout LW = make_wcols_layout(d, wcols_tiles);
   const bool use_wcols = use_cols && !getenv("SC_NO_WCOLS");
   const size_t smem = sizeof(double) * (size_t)L.total;
   // time steps per pass over the state: the records are read and written once per pass, so longer passes amortise the
@@ -629,7 +632,10 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
       double *hd = aux + (size_t)KC * ntb * 8;
       long long grid = (long long)nt * (use_cols ? LC.nc : L.nc);
-      if (use_wcols) grid = ((long long)nt * LW.nt + 3) / 4;
+      if (use_wcols) {
+        grid = ((long long)nt * LW.nitem + 3) / 4;
+        if (!getenv("SC_CHUNK_CTAS")) rk4_per_sm = LW.ntw == 2 ? 2 : 3;
+      }
       if (grid > rk4_per_sm * sm) grid = rk4_per_sm * sm;
       // producer side (caller's stream): this scratch buffer must have been consumed (two batches ago)
       if (overlap && seq >= nbuf) CU(cudaStreamWaitEvent(st, e->ev_lu[buf], 0));
@@ -914,6 +920,105 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
       CU(cudaStreamSynchronize(st));
     }
   }
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------ wavefunction diagnostics (sc_gauss.cuh) ---------
+namespace {
+struct DevBufs {                      // scratch of one diagnostic call
+  std::vector<void *> p;
+  ~DevBufs() { for (void *q : p) cudaFree(q); }
+  template <class T> cudaError_t get(T **out, size_t count) {
+    void *q = nullptr;
+    cudaError_t ce = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
+    if (ce == cudaSuccess) p.push_back(q);
+    *out = static_cast<T *>(q);
+    return ce;
+  }
+};
+cudaError_t launch_gauss_sum(int n_bra, int n_ket, int kp, const double *a, const double *alpha, const double *gamma,
+                             const double *r, const double *s, const double *alphaJ, const double *beta, const double2 *coef,
+                             double2 *out, cudaStream_t st) {
+  const size_t smem = gs_smem_bytes(kp);
+  cudaError_t ce = cudaFuncSetAttribute(k_gauss_sum, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce != cudaSuccess) return ce;
+  k_gauss_sum<<<(n_bra + GS_TI - 1) / GS_TI, GS_THREADS, smem, st>>>(n_bra, n_ket, kp, a, alpha, gamma, r, s, alphaJ, beta, coef, out);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// expansion coefficients v_i of the frozen-Gaussian wavefunction (HermanKlukPropagator.coefficients, propagators.py:657-686)
+extern "C" int sc_engine_coefficients(sc_engine *e, double *v_dev, void *stream) {
+  if (!e || e->dev.n < 1 || !v_dev) return fail(SC_ERR_INVALID, "no ensemble");
+  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "coefficients(): Herman-Kluk propagator only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n;
+  k_coefficients<<<(n + 255) / 256, 256, 0, st>>>(e->dev, 1.0 / (double)e->ntraj_norm, reinterpret_cast<double2 *>(v_dev));
+  CU(cudaGetLastError());
+  return SC_OK;
+}
+
+// |psi|^2 = sum_ij conj(v_i) <q_i,p_i,Gt|q_j,p_j,Gt> v_j (HermanKlukPropagator.norm, propagators.py:734-782).  A, B, C: the
+// (d x d) matrices Gt (2 Gt)^+ Gt, (2 Gt)^+, Gt (2 Gt)^+ of CoherentStatesOverlap(Gt, Gt) (propagators.py:174-179), fac its
+// normalisation factor (:230).  norm2_host[0:2] = Re, Im of the double sum (rank-local when the ensemble is sharded: the
+// caller sums the (n_local x n_total) blocks).
+extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *B_host, const double *C_host, double fac,
+                              double *norm2_host, void *stream) {
+  if (!e || e->dev.n < 1 || !A_host || !B_host || !C_host || !norm2_host) return fail(SC_ERR_INVALID, "norm(): bad arguments");
+  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "norm(): Herman-Kluk propagator only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n, d = e->dev.d, kp = (2 * d + 3) & ~3;
+  DevBufs B;
+  double *mats, *a, *r, *s, *alpha, *beta, *gamma, *res;
+  double2 *v, *o;
+  CU(B.get(&mats, 3 * (size_t)d * d));
+  CU(B.get(&a, (size_t)n * kp)); CU(B.get(&r, (size_t)n * kp)); CU(B.get(&s, (size_t)n * kp));
+  CU(B.get(&alpha, n)); CU(B.get(&beta, n)); CU(B.get(&gamma, n)); CU(B.get(&res, 2));
+  CU(B.get(&v, n)); CU(B.get(&o, n));
+  CU(cudaMemcpyAsync(mats, A_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(mats + d * d, B_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(mats + 2 * d * d, C_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
+  k_coefficients<<<(n + 255) / 256, 256, 0, st>>>(e->dev, 1.0 / (double)e->ntraj_norm, v);
+  CU(cudaGetLastError());
+  k_gauss_prep_norm<<<n, 128, 0, st>>>(e->dev, mats, mats + d * d, mats + 2 * d * d, kp, a, r, s, alpha, beta, gamma);
+  CU(cudaGetLastError());
+  CU(launch_gauss_sum(n, n, kp, a, alpha, gamma, r, s, alpha, beta, v, o, st));
+  k_gauss_dot<<<1, 256, 0, st>>>(n, v, o, res);
+  CU(cudaGetLastError());
+  double h[2];
+  CU(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  norm2_host[0] = fac * h[0];
+  norm2_host[1] = fac * h[1];
+  e->launches += 4;
+  return SC_OK;
+}
+
+// psi(x_k) = sum_i v_i <x_k|q_i,p_i,Gt> on nx grid points (HermanKlukPropagator.wavefunction, propagators.py:688-732);
+// x_dev: (d, nx) like the reference's argument; fac = (det Gt / pi^rank)^(1/4) (propagators.py:279); phi_dev: c128 (nx)
+extern "C" int sc_engine_wavefunction(sc_engine *e, const double *Gt_host, double fac, int nx, const double *x_dev,
+                                      double *phi_dev, void *stream) {
+  if (!e || e->dev.n < 1 || !Gt_host || !x_dev || !phi_dev || nx < 1) return fail(SC_ERR_INVALID, "wavefunction(): bad arguments");
+  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "wavefunction(): Herman-Kluk propagator only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n, d = e->dev.d, kp = (d + 3) & ~3;
+  DevBufs B;
+  double *G, *a, *r, *s, *alpha, *gamma, *alphaJ, *beta;
+  double2 *v;
+  CU(B.get(&G, (size_t)d * d));
+  CU(B.get(&a, (size_t)nx * kp)); CU(B.get(&alpha, nx)); CU(B.get(&gamma, nx));
+  CU(B.get(&r, (size_t)n * kp)); CU(B.get(&s, (size_t)n * kp)); CU(B.get(&alphaJ, n)); CU(B.get(&beta, n));
+  CU(B.get(&v, n));
+  CU(cudaMemcpyAsync(G, Gt_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
+  k_coefficients<<<(n + 255) / 256, 256, 0, st>>>(e->dev, fac / (double)e->ntraj_norm, v);
+  CU(cudaGetLastError());
+  k_gauss_prep_wf_kets<<<n, 128, 0, st>>>(e->dev, G, kp, r, s, alphaJ, beta);
+  CU(cudaGetLastError());
+  k_gauss_prep_wf_bras<<<nx, 128, 0, st>>>(d, nx, x_dev, G, kp, a, alpha, gamma);
+  CU(cudaGetLastError());
+  CU(launch_gauss_sum(nx, n, kp, a, alpha, gamma, r, s, alphaJ, beta, v, reinterpret_cast<double2 *>(phi_dev), st));
+  CU(cudaStreamSynchronize(st));
+  e->launches += 4;
   return SC_OK;
 }
 

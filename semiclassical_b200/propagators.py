@@ -467,6 +467,49 @@ class HermanKlukPropagator(object):
         c, _, signs = self._prefactor_arrays()
         return signs[0] * c
 
+    # ------------------------------------------------------------------ wavefunction diagnostics (propagators.py:657-782)
+    def coefficients(self):
+        """
+        expansion coefficients of the Herman-Kluk wavefunction in the basis of the coherent state trajectories
+        (propagators.py:657-686):  v_i = C_i e^{i S_i} / (2 pi)^d <q_i,p_i|phi(0)> / (ntraj P_i), complex Tensor (ntraj,)
+        """
+        v = torch.empty(self.ntraj, dtype=torch.complex128, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().sc_engine_coefficients(self._engine, v.data_ptr(), self._stream()))
+        return v
+
+    def wavefunction(self, x):
+        """
+        frozen Gaussian approximation of the wavefunction psi(x,t) on a spatial grid (propagators.py:688-732)
+
+        x : real Tensor (dim,nx)   ->   complex numpy.ndarray (nx,)
+        """
+        d, nx = x.shape
+        assert d == self.dim, "spatial grid has wrong dimensions"
+        Gt = self.Gamma_t.detach().to('cpu', torch.float64)
+        _, detG, rank = _pinv_sym(Gt)
+        fac = float((detG / np.pi**rank)**0.25)
+        xg = x.to(device=self.device, dtype=torch.float64).contiguous()
+        phi = torch.empty(nx, dtype=torch.complex128, device=self.device)
+        G = _np(Gt)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().sc_engine_wavefunction(self._engine, _ptr(G), fac, nx, xg.data_ptr(), phi.data_ptr(),
+                                                               self._stream()))
+        return phi.detach().cpu().numpy()
+
+    def norm(self):
+        """
+        norm |psi| = sqrt(sum_ij v_i^* v_j <g_i|g_j>) of the frozen Gaussian wavefunction (propagators.py:734-782);
+        all pairs of trajectories, O(ntraj^2), as two FP64 tensor-core contractions + exp/sincos per pair
+        """
+        cs = CoherentStatesOverlap(self.Gamma_t, self.Gamma_t)
+        A, B, C = _np(cs.Gi_iGij_Gj), _np(cs.iGij), _np(cs.Gj_iGij)
+        out = np.zeros(2)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().sc_engine_norm(self._engine, _ptr(A), _ptr(B), _ptr(C), float(cs.fac), _ptr(out),
+                                                       self._stream()))
+        return float(np.sqrt(out[0]))
+
     def launch_count(self):
         return int(_native.lib().sc_engine_launch_count(self._engine))
 

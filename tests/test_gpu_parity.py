@@ -281,3 +281,42 @@ def test_chunked_path_against_oracle(d, cuda_device):
     assert relerr(pr.y.cpu().numpy(), ref2['y']) < TOL
     assert relerr(pr.c.cpu().numpy(), ref2['c']) < TOL
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
+
+
+# ------------------------------------------------------------------ wavefunction diagnostics (propagators.py:657-782)
+@pytest.mark.parametrize("name", ["diag_as5", "diag_as5_rot", "diag_as24", "diag_1d"])
+def test_wavefunction_diagnostics_match_reference(name, cuda_device):
+    """coefficients(), norm() (all-pairs DMMA kernel), wavefunction(x) after nt steps vs the reference's own values"""
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    pr.propagate(pot, float(g['dt']), int(g['nt']), float(g['energy0_es']))
+    assert relerr(pr.coefficients().cpu().numpy(), g['coefficients']) < TOL
+    assert abs(pr.norm() / float(g['norm']) - 1.0) < TOL
+    phi = pr.wavefunction(T(g['x']))
+    assert phi.shape == g['wavefunction'].shape
+    assert relerr(phi, g['wavefunction']) < TOL
+
+
+def test_norm_against_oracle_ragged(cuda_device):
+    """norm() on an ensemble that is not a multiple of the 64 x 32 tile (n = 203, d = 40: K = 80) vs the numpy oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_synthetic(40)
+    G = np.diag(m.omega)
+    n, nt = 203, 5
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(77))
+    dt, _ = workloads.test_time_grid()
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi, probi, dt, nt,
+                     m.en_zpt)
+    d = 40
+    qpS = np.concatenate((ref['y'][:2 * d], ref['y'][-1:]), axis=0)
+    v = oracle.hk_coefficients(G, G, m.q0, m.p0, zi, probi, qpS, ref['c'], ref['signs'][0])
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    pr.propagate(pot, dt, nt, m.en_zpt)
+    assert relerr(pr.coefficients().cpu().numpy(), v) < TOL
+    assert abs(pr.norm() / oracle.hk_norm(G, qpS, v) - 1.0) < TOL
+    x = m.q0[:, None] + 0.05 * np.random.default_rng(5).standard_normal((d, 19))
+    assert relerr(pr.wavefunction(T(x)), oracle.hk_wavefunction(G, qpS, v, x)) < TOL
