@@ -1,0 +1,182 @@
+"""
+Driver of the `dynamics` task of `semi` (cli.run_semiclassical_dynamics, cli.py:171-476) on top of the B200 engine.
+
+Same JSON task, same `correlations.npz` (keys, running average over repetitions, `overwrite=false` accumulation, the
+`times = linspace(0, nt dt, nt)` grid of cli.py:310-311 whose spacing is not dt, NaN guard, C(0) = 1 check), but the
+time loop {autocorrelation; ic_correlation; step} x nt of one repetition (cli.py:401-436, two host syncs per step)
+becomes a few fused launches of `steps_per_launch` time steps, and a repetition may be as large as the GPU memory
+allows (116 KB per trajectory at 60 modes) instead of the reference's 10^4.  With torch.distributed initialised
+(one process per GPU) every repetition is sharded over the ranks and combined by one all-reduce per launch
+(semiclassical_b200.distributed); rank 0 writes the file.
+
+Model potentials ("anharmonic AS") need nothing else.  Molecular potentials ("harmonic", "gdml") read Gaussian
+formatted checkpoint files: pass the reference's `semiclassical.readers` module (or anything with the same
+`FormattedCheckpointFile` interface, readers.py) as `readers=`; parsing fchk files is setup-time host work and out
+of the scope of this package.
+"""
+import logging
+import os
+
+import numpy as np
+import torch
+
+from semiclassical_b200 import potentials, propagators, units
+from semiclassical_b200.units import hbar
+
+logger = logging.getLogger(__name__)
+
+
+class ConfigurationError(Exception):
+    pass
+
+
+def _as_model(model_file):
+    """frequencies, displacements, NACs and anharmonicities of an adiabatic-shift model file (cli.py:229-283)"""
+    data = torch.from_numpy(np.loadtxt(model_file))
+    if len(data.shape) == 1:
+        data = torch.reshape(data, (1, -1))
+    omega = data[:, 0] / units.hartree_to_wavenumbers
+    S = data[:, 1]
+    nac = data[:, 2]
+    dQ = torch.sqrt(2.0 * abs(S) / omega) * torch.sign(S)
+    dQ[omega == 0.0] = 0.0
+    chi = data[:, 3]
+    potential = potentials.MorsePotential(omega, chi, nac)
+    return potential, dQ, 0.0 * dQ, torch.diag(omega), torch.sum(hbar / 2.0 * omega).item()
+
+
+def _molecular(p, readers):
+    if readers is None:
+        try:
+            from semiclassical import readers  # the reference package, if it is installed next to this one
+        except Exception as err:
+            raise ConfigurationError(f"potential type '{p['type']}' reads formatted checkpoint files: pass readers= "
+                                     f"(semiclassical.readers is not importable: {err})")
+    with open(p['coupling']) as f:
+        nacs_fchk = readers.FormattedCheckpointFile(f)
+    if p['type'] == "harmonic":
+        with open(p['ground']) as f:
+            freq_fchk = readers.FormattedCheckpointFile(f)
+        potential = potentials.MolecularHarmonicPotential(freq_fchk, nacs_fchk)
+    else:
+        potential = potentials.MolecularGDMLPotential(np.load(p['ground'], allow_pickle=True), nacs_fchk)
+    with open(p['excited']) as f:
+        excited_fchk = readers.FormattedCheckpointFile(f)
+    x0, Gamma_0, en_zpt = excited_fchk.vibrational_groundstate()
+    q0 = torch.from_numpy(x0)
+    return potential, q0, torch.zeros_like(q0), torch.from_numpy(Gamma_0), en_zpt, excited_fchk
+
+
+def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None, steps_per_launch=20):
+    """
+    Parameters
+    ----------
+    task      : JSON structure of one `"task": "dynamics"` entry (cli.py:171)
+    device    : CUDA device (there is no CPU path)
+    readers   : module providing FormattedCheckpointFile for molecular potentials
+    ensembles : optional list of (zi (2 dim, n), probi (n,)) per repetition injected instead of sampling
+                (parity tests: the reference's RNG stream is device dependent)
+
+    Returns the dictionary that was written to the npz file (rank 0; other ranks return the same arrays).
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    p = task['potential']
+    excited_fchk = None
+    if p['type'] in ("harmonic", "gdml"):
+        potential, q0, p0, Gamma_0, en_zpt, excited_fchk = _molecular(p, readers)
+    elif p['type'] == "anharmonic AS":
+        potential, q0, p0, Gamma_0, en_zpt = _as_model(p['model_file'])
+    else:
+        raise ConfigurationError(f"Unknown potential type in {task['potential']}")
+    if hasattr(potential, "minimize"):
+        logger.info("find minimum on final potential energy surface")
+        potential.minimize(q0)
+    adiabatic_gap = (excited_fchk.total_energy() - potential.total_energy()) if excited_fchk is not None else np.nan
+    Gamma_i = Gamma_t = Gamma_0
+
+    dt = task['time_step_fs'] / units.autime_to_fs
+    nt = task['num_steps']
+    times = torch.linspace(0.0, nt * dt, nt)
+    batch_size = task.get('batch_size', 10000)
+    num_trajectories = task.get('num_trajectories', 50000)
+    num_repetitions = max(num_trajectories // batch_size, 1)
+    num_samples = min(batch_size, num_trajectories)
+    propagator_name = task.get('propagator', 'HK')
+
+    filename = task['results'].get('correlations', 'correlations.npz')
+    if rank == 0:
+        if task['results'].get('overwrite', True) is True or (not os.path.exists(filename)):
+            np.savez(filename, propagator=propagator_name, times=times, autocorrelation=np.zeros((nt,), dtype=complex),
+                     ic_correlation=np.zeros((nt,), dtype=complex), adiabatic_gap=adiabatic_gap, zero_point_energy=en_zpt,
+                     trajectories=0)
+        else:
+            assert task.get('manual_seed', None) is None, \
+                "Multiple runs with the same sequence of random numbers make no sense! Do not use `manual_seed` and `overwrite=False` at the same time"
+            data = np.load(filename)
+            assert np.array_equal(data['times'], times.numpy()), \
+                f"Time steps in {filename} differ. Delete the old file or change the grid for time propagation."
+            assert data['propagator'] == propagator_name, "Data produced with different propagators cannot be added."
+    seed = task.get('manual_seed', None)
+    if seed is not None:
+        logger.warning("The random number generator should not be seeded manually unless for debugging!")
+        torch.manual_seed(seed + rank)
+    calc_norm_every = task.get('calc_norm_every', 0)
+    group = True if world > 1 else None
+
+    data = None
+    for repetition in range(num_repetitions):
+        logger.info(f"*** Repetition {repetition+1} ***")
+        if propagator_name == "WM":
+            alpha = task.get('cell_width', 10000.0)
+            propagator = propagators.WaltonManolopoulosPropagator(Gamma_i, Gamma_t, alpha, alpha, device=device)
+        else:
+            propagator = propagators.HermanKlukPropagator(Gamma_i, Gamma_t, device=device)
+        lo, hi = rank * num_samples // world, (rank + 1) * num_samples // world
+        if ensembles is not None:
+            zi, probi = ensembles[repetition]
+            propagator.set_ensemble(q0, p0, Gamma_0, torch.as_tensor(zi)[:, lo:hi], torch.as_tensor(probi)[lo:hi],
+                                    ntraj_total=num_samples)
+        else:
+            propagator.initial_conditions(q0, p0, Gamma_0, ntraj=hi - lo, ntraj_total=num_samples)
+        autocorrelation_ = np.zeros((nt,), dtype=complex)
+        ic_correlation_ = np.zeros((nt,), dtype=complex)
+        # t = 0 from the installed ensemble, then fused launches; a launch ends where the norm is due
+        first = torch.tensor([complex(propagator.autocorrelation(energy0_es=en_zpt)),
+                              complex(propagator.ic_correlation(potential, energy0_es=en_zpt))], device=propagator.device)
+        if world > 1:
+            first = torch.view_as_real(first).contiguous()
+            dist.all_reduce(first)
+            first = torch.view_as_complex(first)
+        autocorrelation_[0], ic_correlation_[0] = (complex(x) for x in first.cpu().numpy())
+        t = 0
+        while True:
+            if calc_norm_every > 0 and t % calc_norm_every == 0 and world == 1:
+                norm = propagator.norm()
+                logger.info(f" time/fs= {times[t]*units.autime_to_fs}  norm= {norm:9.6f}")
+            if t == nt - 1:
+                break
+            k = min(steps_per_launch, nt - 1 - t)
+            if calc_norm_every > 0:
+                k = min(k, calc_norm_every - t % calc_norm_every)
+            a, i = propagator.propagate(potential, dt, k, energy0_es=en_zpt, group=group)
+            autocorrelation_[t + 1:t + 1 + k], ic_correlation_[t + 1:t + 1 + k] = a, i
+            t += k
+            assert not np.isnan(autocorrelation_).any(), f"encountered NaN's in autocorrelation : {autocorrelation_}"
+            assert not np.isnan(ic_correlation_).any(), f"encountered NaN's in IC correlation : {ic_correlation_}"
+        # the last step() of the reference loop only advances the state, its correlations are never read (cli.py:436)
+        if rank == 0:
+            data = dict(np.load(filename))
+            ntraj_old, ntraj_new = data['trajectories'], num_samples
+            ntraj_tot = ntraj_old + ntraj_new
+            autocorrelation = (ntraj_new * autocorrelation_ + ntraj_old * data['autocorrelation']) / ntraj_tot
+            ic_correlation = (ntraj_new * ic_correlation_ + ntraj_old * data['ic_correlation']) / ntraj_tot
+            logger.info(f"<phi(0)|phi(0)>= {autocorrelation[0]}")
+            assert abs(autocorrelation[0] - 1.0) < 1.0e-3
+            data['trajectories'] = ntraj_tot
+            data['autocorrelation'] = autocorrelation
+            data['ic_correlation'] = ic_correlation
+            data.pop('ic_rate', None)
+            np.savez(filename, **data)
+    return data

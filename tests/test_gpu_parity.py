@@ -320,3 +320,42 @@ def test_norm_against_oracle_ragged(cuda_device):
     assert abs(pr.norm() / oracle.hk_norm(G, qpS, v) - 1.0) < TOL
     x = m.q0[:, None] + 0.05 * np.random.default_rng(5).standard_normal((d, 19))
     assert relerr(pr.wavefunction(T(x)), oracle.hk_wavefunction(G, qpS, v, x)) < TOL
+
+
+# ------------------------------------------------------------------ `semi dynamics` driver (cli.py:171-476)
+def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
+    """the JSON-task driver on the 5-mode AS fixture with the reference's ensemble injected: same correlations.npz
+    content as the reference loop (golden), running average over repetitions, times grid quirk, overwrite=false"""
+    from semiclassical_b200 import dynamics, units, workloads
+    g = helpers.load_golden("hk_as5_chi002")
+    m = workloads.as_5modes(0.02)
+    model_file = tmp_path / "AS_model.dat"
+    rows = workloads._AS5_ROWS
+    np.savetxt(model_file, np.column_stack((rows, np.full(len(rows), 0.02))), fmt="%.10f",
+               header="omega/cm^-1  Huang-Rhys  NAC  chi")
+    nt, n = int(g['nt']), len(g['probi'])
+    out = tmp_path / "correlations.npz"
+    task = {"task": "dynamics", "potential": {"type": "anharmonic AS", "model_file": str(model_file)}, "propagator": "HK",
+            "batch_size": n, "num_trajectories": n, "num_steps": nt, "time_step_fs": float(g['dt']) * units.autime_to_fs,
+            "results": {"correlations": str(out)}}
+    dynamics.run_semiclassical_dynamics(task, device=cuda_device, ensembles=[(g['zi'], g['probi'])], steps_per_launch=17)
+    data = dict(np.load(out))
+    assert relerr(data['autocorrelation'], g['autocorrelation']) < TOL
+    assert relerr(data['ic_correlation'], g['ic_correlation']) < TOL
+    assert int(data['trajectories']) == n and str(data['propagator']) == "HK"
+    assert np.allclose(data['times'], np.linspace(0.0, nt * float(g['dt']), nt), rtol=1e-12)
+    assert abs(float(data['zero_point_energy']) - m.en_zpt) < 1e-12
+    # second run accumulates into the same file: identical ensemble -> identical averages, doubled count
+    task["results"]["overwrite"] = False
+    dynamics.run_semiclassical_dynamics(task, device=cuda_device, ensembles=[(g['zi'], g['probi'])])
+    data2 = dict(np.load(out))
+    assert int(data2['trajectories']) == 2 * n
+    assert relerr(data2['autocorrelation'], data['autocorrelation']) < 1.0e-13
+    # sampled on the device (torch CUDA generator): C(0) = 1 and the statistical agreement the reference tests ask for
+    task["results"]["overwrite"] = True
+    task["manual_seed"] = 0
+    task["calc_norm_every"] = 50
+    dynamics.run_semiclassical_dynamics(task, device=cuda_device)
+    data3 = dict(np.load(out))
+    assert abs(data3['autocorrelation'][0] - 1.0) < 1.0e-9
+    assert relerr(data3['autocorrelation'], g['autocorrelation']) < 0.2
