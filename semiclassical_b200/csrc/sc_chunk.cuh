@@ -872,6 +872,9 @@ static cudaError_t launch_wcols_t(int grid, size_t smem, const EngDev &E, const 
                                   double2 *cm, const double *hd, const WColsLayout &L, cudaStream_t st) {
   cudaError_t ce = cudaFuncSetAttribute(k_rk4_wcols<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
+  // full shared-memory carve-out: CTAs of the LU kernel can become resident next to this kernel's without an SM re-configuration
+  ce = cudaFuncSetAttribute(k_rk4_wcols<NK, NTW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce != cudaSuccess) return ce;
   k_rk4_wcols<NK, NTW><<<grid, 128, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
   return cudaGetLastError();
 }

@@ -112,6 +112,7 @@ struct sc_engine {
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
   long long ntraj_norm = 0;
+  int ens_n = 0;                  // size of the ensemble the buffers in `ens` were allocated for
   long long launches = 0;
   int sm_count = 148;
   const char *kernel_name = "none";
@@ -750,22 +751,29 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   EngDev &D = e->dev;
   const int d = D.d;
   CU(cudaStreamSynchronize(st));
-  e->ens.release();  // the previous ensemble
-  e->stage_buf = nullptr;
-  D.n = n;
-  D.qps = (2 * d + 1 + 1) & ~1;
-  D.rs = D.qps + 4 * d * d;
   e->ntraj_norm = ntraj_norm > 0 ? ntraj_norm : n;
-  double *zt = nullptr;
-  double2 *wvi = nullptr;
-  CU(e->ens.alloc((size_t)n * D.rs, &D.rec));
-  CU(e->ens.alloc((size_t)n * 2 * d, &zt));
-  CU(e->ens.alloc((size_t)n, &wvi));
-  CU(e->ens.alloc((size_t)n, &D.c2));
-  CU(e->ens.alloc((size_t)n, &D.c));
-  CU(e->ens.alloc((size_t)n, &D.sign));
-  D.zt = zt;
-  D.wvi = wvi;
+  double *zt = const_cast<double *>(D.zt);
+  double2 *wvi = const_cast<double2 *>(D.wvi);
+  // a new ensemble of the same size (the next repetition of a run) reuses the device buffers: allocating and freeing
+  // 116 KB per trajectory costs more than initialising them
+  const bool reuse = !e->cfg.wm && e->ens_n == n && !e->ens.ptrs.empty() && !e->stage_buf;
+  if (!reuse) {
+    e->ens.release();  // the previous ensemble
+    e->stage_buf = nullptr;
+    e->ens_n = 0;
+    D.n = n;
+    D.qps = (2 * d + 1 + 1) & ~1;
+    D.rs = D.qps + 4 * d * d;
+    CU(e->ens.alloc((size_t)n * D.rs, &D.rec));
+    CU(e->ens.alloc((size_t)n * 2 * d, &zt));
+    CU(e->ens.alloc((size_t)n, &wvi));
+    CU(e->ens.alloc((size_t)n, &D.c2));
+    CU(e->ens.alloc((size_t)n, &D.c));
+    CU(e->ens.alloc((size_t)n, &D.sign));
+    D.zt = zt;
+    D.wvi = wvi;
+    e->ens_n = n;
+  }
   CU(cudaMemsetAsync(D.c2, 0, sizeof(double2) * n, st));
   CU(cudaMemsetAsync(D.c, 0, sizeof(double2) * n, st));
   CU(cudaMemsetAsync(D.sign, 0, sizeof(double) * n, st));

@@ -83,6 +83,8 @@ static cudaError_t launch_lu_batch(const double2 *mats, int dr, int nmat, double
     const size_t smem = lum_smem_bytes(dr);
     cudaError_t ce = cudaFuncSetAttribute(k_lu_mma<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (ce != cudaSuccess) return ce;
+    ce = cudaFuncSetAttribute(k_lu_mma<4, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (ce != cudaSuccess) return ce;
     int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 3);
     if (grid > nmat) grid = nmat;
     k_lu_mma<4, 3><<<grid, 128, smem, st>>>(mats, dr, nmat, det_out);

@@ -151,6 +151,10 @@ class HermanKlukPropagator(object):
         Gi = self.Gamma_i.detach().to('cpu', torch.float64)
         Gt = self.Gamma_t.detach().to('cpu', torch.float64)
         d = G0.shape[0]
+        # same wavepacket as last time (a new repetition of the same run): keep the engine and its device buffers
+        key = (_np(q0).tobytes(), _np(p0).tobytes(), _np(G0).tobytes(), self._wm, float(self.alpha), float(self.beta))
+        if self._engine is not None and getattr(self, '_const_key', None) == key:
+            return self._const_dims
         # non-zero subspace of Gi + G0 and its pseudo-inverse (propagators.py:493-501)
         wp, Vp = _eigh(Gi + G0)
         nzp = wp > ZERO
@@ -199,6 +203,7 @@ class HermanKlukPropagator(object):
             _native.check(_native.lib().sc_engine_create(ctypes.byref(eng), ctypes.byref(cfg)))
         self._engine = eng
         self._iLz_detLz = None
+        self._const_key, self._const_dims = key, (d, dr)
         return d, dr
 
     def initial_conditions(self, q0, p0, Gamma_0, ntraj=5000, ntraj_total=None):

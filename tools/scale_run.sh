@@ -1,0 +1,14 @@
+# 1/2/4/8-GPU bench lines of the round, back to back on one box (launched as the driver does)
+python bench.py --gpus 1 --steps 10 --warmup 3 > gpurun_out/scale_r01g_n1.json 2> gpurun_out/scale_r01g_n1.err
+for n in 2 4 8; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/scale_r01g_n$n.json 2> gpurun_out/scale_r01g_n$n.err
+done
+for n in 1 2 4 8; do python - <<PY
+import json
+try:
+    j = json.loads([l for l in open("gpurun_out/scale_r01g_n$n.json") if l.startswith("{")][-1])
+    print($n, j["value"], j["e2e"]["value"], j["roofline"]["whole_step"]["frac"])
+except Exception as e:
+    print($n, "FAILED", e)
+PY
+done
