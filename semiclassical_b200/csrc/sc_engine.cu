@@ -681,6 +681,63 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   return SC_OK;
 }
 
+// k_hk_mma in split mode + batched LU + finish kernel: the general (dense Gamma, any native potential) path for
+// 17 <= d <= 62.  Same batching as run_hk_chunked: windows of ntb trajectories x passes of KC steps, scratch for the
+// prefactor matrices of one window.
+static int run_hk_mma_split(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st,
+                            const LaunchPlan &pl) {
+  const int n = e->dev.n, dr = e->dev.dr, sm = e->sm_count;
+  int KC = 16;
+  if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
+  if (KC > MMA_KMAX) KC = MMA_KMAX;
+  {
+    const int npass = (nsteps + KC - 1) / KC;
+    KC = (nsteps + npass - 1) / npass;
+  }
+  const size_t per_traj = (size_t)KC * ((size_t)dr * dr * sizeof(double2) + sizeof(double2) + 8 * sizeof(double));
+  size_t budget = (size_t)3 << 30;
+  if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
+  long long ntb = (long long)(budget / per_traj);
+  ntb = (ntb / sm) * sm;
+  if (ntb < sm) ntb = sm;
+  if (ntb > n) ntb = n;
+  const size_t need_bytes = per_traj * (size_t)ntb + 512;
+  if (need_bytes > e->chunk_scratch_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
+    e->chunk_scratch = nullptr;
+    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
+    e->chunk_scratch_cap = need_bytes;
+  }
+  double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
+  double2 *det = cm + (size_t)KC * ntb * dr * dr;
+  double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
+  size_t ngroups = 0;
+  for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
+  if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
+  for (int s0 = 0; s0 < nsteps; s0 += KC) {
+    const int ks = std::min(KC, nsteps - s0);
+    size_t g0 = 0;
+    for (long long t0 = 0; t0 < n; t0 += ntb) {
+      const int nt = (int)std::min<long long>(ntb, n - t0);
+      const int grid = std::min(nt, pl.grid);
+      cudaError_t ce = launch_mma(grid, pl.threads, pl.smem, e->dev, P, h, ks, nullptr, pl.L, st, (int)t0, nt, cm, aux);
+      if (ce != cudaSuccess) return fail(SC_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(ce));
+      CU(launch_lu_batch(cm, dr, ks * nt, det, sm, 0, st));
+      const int nblk = (nt + 127) / 128;
+      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
+      CU(cudaGetLastError());
+      g0 += nblk;
+      e->launches += 3;
+    }
+  }
+  k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  e->kernel_name = dr > 32 ? "k_hk_mma+k_lu_mma+k_hk_finish" : "k_hk_mma+k_lu_batch+k_hk_finish";
+  return SC_OK;
+}
+
 static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, int mode, double *out_dev, cudaStream_t st,
                          bool allow_mma = true) {
   LaunchPlan pl;
@@ -700,6 +757,7 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
   }
   if (mode != MODE_INIT && mode != MODE_TRACK && !pl.mma) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
   cudaError_t ce = cudaSuccess;
+  if (pl.mma && mode == MODE_STEP && !getenv("SC_MMA_FUSED_LU")) return run_hk_mma_split(e, P, h, nsteps, out_dev, st, pl);
   if (pl.mma) {
     ce = launch_mma(pl.grid, pl.threads, pl.smem, e->dev, P, h, nsteps, e->partials, pl.L, st);
     e->kernel_name = "k_hk_mma";

@@ -268,6 +268,11 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
       WJ[T * 32 + swl] = nxt[T];
     }
     unsigned long long done = pad_rows;
+    // next block of this warp (or its first block of the CTA's next matrix): the loads are issued when the warp first
+    // has to wait for a panel (it is ahead of the factorisation front, i.e. about to be on the critical path, and the
+    // address arithmetic costs nothing there), else right before its own panel; they fly during the factorisation
+    bool prefetched = false;
+    const bool same = J + NW < nblocks;
     LUM_T0()
 #pragma unroll 1
     for (int K = 0; K < J; ++K) {
@@ -280,6 +285,10 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
         }
 #else
         if (known <= K) {
+          if (!prefetched) {
+            lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
+            prefetched = true;
+          }
           flow_bar_wait(&sh->bar[K], parity);
           known = K + 1;
         }
@@ -288,16 +297,16 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
       LUM_T(0)
       const int pk = sh->p[K][j];
       const unsigned full = sh->tmask[K];
-      __syncwarp();                                              // mirror stores of the previous update are visible
-      const double2 x = WJ[pk * 4 + (jj ^ ((pk >> 1) & 3))];     // X[k = j][jj]
-      __syncwarp();                                              // ... and read before this update overwrites them
-      const double b0 = part ? -x.y : -x.x, b1 = part ? -x.x : x.y;
       const double2 *Wk = W + (size_t)K * LUM_PANEL_ELEMS + swl;
-      // the two k-steps of a tile are dependent (26 cycles); issue all first k-steps, then all second ones
       double2 wv[8];
 #pragma unroll
       for (int T = 0; T < 8; ++T)
         if (!((full >> T) & 1u)) wv[T] = Wk[T * 32];             // warp-uniform: some row of this tile is still active
+      __syncwarp();                                              // mirror stores of the previous update are visible
+      const double2 x = WJ[pk * 4 + (jj ^ ((pk >> 1) & 3))];     // X[k = j][jj]
+      __syncwarp();                                              // ... and read before this update overwrites them
+      const double b0 = part ? -x.y : -x.x, b1 = part ? -x.x : x.y;
+      // the two k-steps of a tile are dependent (26 cycles); issue all first k-steps, then all second ones
 #ifndef LUM_SKIP_UPD
 #pragma unroll
       for (int T = 0; T < 8; ++T)
@@ -312,11 +321,7 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
       LUM_T(1)
     }
     if (J > 0) done = sh->dmask[J - 1];
-    // next block of this warp (or its first block of the CTA's next matrix): the loads fly during the factorisation
-    {
-      const bool same = J + NW < nblocks;
-      lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
-    }
+    if (!prefetched) lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
     // the mirror is the transpose into the rows <-> lanes layout: factor, publish
     __syncwarp();
 #ifdef LUM_SKIP_PANEL

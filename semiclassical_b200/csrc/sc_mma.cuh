@@ -94,7 +94,13 @@ __device__ __forceinline__ double pot_local_vals(const PotDev &P, int t, double 
 
 template <int WM, int WN, int NWM, int NWN, int MC>
 __global__ void __launch_bounds__(32 * NWM * NWN, 1)
-k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, double *partials, SmemLayout L) {
+k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, double *partials, SmemLayout L, int traj0,
+         int ntw, double2 *__restrict__ cm, double *__restrict__ aux) {
+  // cm != nullptr ("split" mode): the prefactor matrix of every (step, trajectory) of the window [traj0, traj0 + ntw)
+  // goes to cm[(step ntw + tl) dr^2 ...] (LU column a, LU row b at [a dr + b]) and the overlap / action / energy sums
+  // to aux[(step ntw + tl) 8 ...]; the determinants are taken by the batched DMMA LU (sc_lu_mma.cuh) and the branch
+  // tracking + contributions by k_hk_finish -- the in-kernel register LU was 59 % of the fused step.
+  const bool split = cm != nullptr;
   constexpr int NW = NWM * NWN, TPT = 32 * NW;
   extern __shared__ __align__(16) double smem[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -121,7 +127,8 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
   for (int i = t; i < 5 * nsteps; i += TPT) cacc[i] = 0.0;
   for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
   PT_DECL
-  for (int traj = gg; traj < E.n; traj += NG) {
+  for (int tl = gg; tl < ntw; tl += NG) {
+    const int traj = traj0 + tl;
     double *rec = E.rec + (size_t)traj * E.rs;
     if (t < d) { q[t] = rec[t]; p[t] = rec[d + t]; }
     double S = rec[2 * d];
@@ -357,9 +364,29 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
         }
       }
       PT(4);
-      const double2 det = lu_det_regs<NW, MC, 0>(lo, hi, dr, lush, warp, lane);
+      if (split) {
+        double2 *mat = cm + ((size_t)step * ntw + tl) * dr * dr;
+#pragma unroll
+        for (int m = 0; m < MC; ++m) {
+          const int a = warp + NW * m;
+          if (a < dr) {
+            if (lane < dr) mat[a * dr + lane] = lo[m];
+            if (lane + 32 < dr) mat[a * dr + lane + 32] = hi[m];
+          }
+        }
+        __syncthreads();                                      // red[] of warps 0 and 1 is complete
+        if (t == 0) {                                         // only thread 0 carries the action
+          S += h / 6.0 * (red[12] + red[13]);
+          double *ax = aux + ((size_t)step * ntw + tl) * 8;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ax[i] = red[i * 2] + red[i * 2 + 1];
+          ax[6] = S;
+          ax[7] = red[14] + red[15];
+        }
+      }
+      const double2 det = split ? make_double2(1.0, 0.0) : lu_det_regs<NW, MC, 0>(lo, hi, dr, lush, warp, lane);
       PT(5);
-      if (t == 0) {
+      if (t == 0 && !split) {
         double v6[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) v6[i] = red[i * 2] + red[i * 2 + 1];
@@ -394,9 +421,11 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
     if (t < d) { rec[t] = q[t]; rec[d + t] = p[t]; }
     if (t == 0) {
       rec[2 * d] = S;
-      E.c2[traj] = c2;
-      E.c[traj] = cc;
-      E.sign[traj] = sign;
+      if (!split) {
+        E.c2[traj] = c2;
+        E.c[traj] = cc;
+        E.sign[traj] = sign;
+      }
     }
     for (int idx = t; idx < NE; idx += TPT) {
       const int a = idx / W, b = idx % W;
@@ -407,8 +436,9 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
     PT(8);
   }
   // per-CTA correlation sums of this launch (each row is written by exactly one CTA: no memset, no atomics)
-  for (int i = t; i < 5 * nsteps; i += TPT)
-    partials[((size_t)gg * nsteps_total + step0 + i / 5) * 5 + i % 5] = cacc[i];
+  if (!split)
+    for (int i = t; i < 5 * nsteps; i += TPT)
+      partials[((size_t)gg * nsteps_total + step0 + i / 5) * 5 + i % 5] = cacc[i];
 }
 
 // ------------------------------------------------------------------ host-side dispatch -------
@@ -442,15 +472,18 @@ static int mma_threads(int d) {
   return 32 * c.nwm * c.nwn;
 }
 
+// cm == nullptr: fused mode over the whole ensemble (launches of at most MMA_KMAX steps); else split mode: ONE launch of
+// nsteps <= MMA_KMAX steps over the window [traj0, traj0 + ntw)
 template <int WM, int WN, int NWM, int NWN, int MC>
 static cudaError_t launch_mma_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps,
-                                double *partials, const SmemLayout &L, cudaStream_t st) {
+                                double *partials, const SmemLayout &L, cudaStream_t st, int traj0, int ntw, double2 *cm,
+                                double *aux) {
   auto kern = k_hk_mma<WM, WN, NWM, NWN, MC>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
   for (int s0 = 0; s0 < nsteps; s0 += MMA_KMAX) {
     const int ns = (nsteps - s0 < MMA_KMAX) ? nsteps - s0 : MMA_KMAX;
-    kern<<<grid, 32 * NWM * NWN, smem, st>>>(E, P, h, ns, s0, nsteps, partials, L);
+    kern<<<grid, 32 * NWM * NWN, smem, st>>>(E, P, h, ns, s0, nsteps, partials, L, traj0, ntw, cm, aux);
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return ce;
   }
@@ -458,14 +491,16 @@ static cudaError_t launch_mma_t(int grid, size_t smem, const EngDev &E, const Po
 }
 
 static cudaError_t launch_mma(int grid, int threads, size_t smem, const EngDev &E, const PotDev &P, double h,
-                              int nsteps, double *partials, const SmemLayout &L, cudaStream_t st) {
+                              int nsteps, double *partials, const SmemLayout &L, cudaStream_t st, int traj0 = 0, int ntw = -1,
+                              double2 *cm = nullptr, double *aux = nullptr) {
   MmaConfig c;
   if (!mma_config(E.d, c) || threads != 32 * c.nwm * c.nwn) return cudaErrorInvalidValue;
+  if (ntw < 0) ntw = E.n;
   // last parameter: LU columns per thread = ceil(max d of the bucket / warps)
-  if (E.d <= 32) return launch_mma_t<2, 2, 2, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
-  if (E.d <= 48) return launch_mma_t<2, 3, 3, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
-  if (E.d <= 60) return launch_mma_t<2, 5, 4, 3, 5>(grid, smem, E, P, h, nsteps, partials, L, st);
-  return launch_mma_t<2, 4, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st);
+  if (E.d <= 32) return launch_mma_t<2, 2, 2, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st, traj0, ntw, cm, aux);
+  if (E.d <= 48) return launch_mma_t<2, 3, 3, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st, traj0, ntw, cm, aux);
+  if (E.d <= 60) return launch_mma_t<2, 5, 4, 3, 5>(grid, smem, E, P, h, nsteps, partials, L, st, traj0, ntw, cm, aux);
+  return launch_mma_t<2, 4, 4, 4, 4>(grid, smem, E, P, h, nsteps, partials, L, st, traj0, ntw, cm, aux);
 }
 
 }  // namespace sc
