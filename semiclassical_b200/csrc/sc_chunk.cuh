@@ -1,58 +1,30 @@
-// sc_chunk.cuh -- column-chunked Herman-Kluk step for large d with diagonal width matrices (the headline path).
+// sc_chunk.cuh -- column pipeline of the Herman-Kluk step for large d with diagonal width matrices (the headline path).
 //
 // The 2d columns of the monodromy blocks are independent linear ODEs driven by the same Hessians
 // (propagators.py:342-357: d/dt [Mqq;Mpq][:,b] and d/dt [Mqp;Mpp][:,b] only involve column b), and with diagonal
 // Gamma column b of the prefactor matrix (propagators.py:969-986) needs exactly column b of the four blocks.  The
-// step is therefore split into three throughput kernels:
+// step is therefore split into throughput kernels:
 //
-//   k_rk4_chunk   work item = (trajectory, chunk of nb columns b): a 128-thread CTA keeps U = [Mqq|Mqp][:, chunk],
-//                 V = [Mpq|Mpp][:, chunk] (d x 2nb each) and the dense Hessian in ~72 KB of shared memory for K time
-//                 steps -> THREE independent CTAs per SM, so one CTA's elementwise / barrier / potential phases
-//                 overlap the other CTAs' DMMA.  H U_s runs on the FP64 tensor pipe (mma.sync.m8n8k4.f64), the RK4
-//                 accumulators stay in registers, and the stage operand U_s is formed IN PLACE:
+//   k_qp_path     (q, p, S) of the separable model for K steps, one warp per trajectory: Hessian diagonals of every
+//                 stage, overlap / NAC partial sums, action, T+V.
+//   k_rk4_wcols   work item = (trajectory, tile of 4 columns b) owned by ONE warp for K steps: the warp's 60 x 8 slab
+//                 of U = [Mqq|Mqp] is the B operand of H U_s (mma.sync.m8n8k4.f64) and the set of elements it updates;
+//                 RK4 accumulators in registers, stage operand formed IN PLACE:
 //                     U_2 = U + h/2 V/m,  U_3 = U_2 + h^2/4 kv_1/m,  U_4 = U_3 + [h/2 V + h^2/2 kv_2 - h^2/4 kv_1]/m,
 //                     U'  = U_4 + [h^2/6 (kv_1+kv_2+kv_3) - h^2/2 kv_2]/m,   V' = V + h/6 (kv_1+2kv_2+2kv_3+kv_4)
-//                 (kv_s = -H_s U_s; algebraically the classical RK4 of propagators.py:114-119).  Every step the CTA
-//                 writes its nb columns of the complex prefactor matrix to a global scratch; chunk 0 also writes the
-//                 overlap / NAC partial sums, the action and T+V.
-//   k_lu_batch    (sc_lu_batch.cuh) determinants of all (step, trajectory) matrices of the batch.
+//                 (kv_s = -H_s U_s; algebraically the classical RK4 of propagators.py:114-119).  H_s = H0 + diag(h_s):
+//                 the dense base H0 (shared memory, zero for the separable models served here) is multiplied in
+//                 full, the stage diagonal is added to the A fragment of the diagonal tile.  Every step the warp
+//                 writes its 4 columns of the complex prefactor matrix to a global scratch.
+//   k_lu_mma      (sc_lu_mma.cuh, sc_lu_batch.cuh) determinants of all (step, trajectory) matrices of the batch.
 //   k_hk_finish   per trajectory, in time order: sqrt branch tracking (propagators.py:1045-1047), contributions to
 //                 C_auto and k_ic (propagators.py:784-911), deterministic per-block partial sums.
-//
-// Every chunk CTA integrates (q, p) itself (separable potentials: d threads, no dependence on M); that is 3x
-// redundant work of O(d) per step against O(d^3)/3 of monodromy work.
+// Layout of a slab in shared memory: row-major [row][8]; B-fragment loads (4 rows x 8 columns = 256 contiguous
+// bytes) and the 128-bit owner accesses (8 rows x 64 bytes) are conflict free without swizzling.
 #pragma once
 #include "sc_mma.cuh"
 
 namespace sc {
-
-struct ChunkLayout {
-  int nc, nb, ldu, ldh, dk;                 // chunks per trajectory, columns b per chunk, leading dimensions, K padding
-  int off_U, off_V, off_H, off_vec, total;  // doubles
-};
-
-__host__ __device__ inline ChunkLayout make_chunk_layout(int d) {
-  ChunkLayout L;
-  L.nc = (d <= 60) ? 3 : 4;
-  L.nb = (d + L.nc - 1) / L.nc;
-  int w = 2 * L.nb;
-  w = (w + 7) & ~7;                          // whole n-tiles
-  L.ldu = w;
-  while (L.ldu % 16 != 8) L.ldu += 8;
-  L.dk = (d + 3) & ~3;
-  L.ldh = L.dk;
-  while (L.ldh % 16 != 4 && L.ldh % 16 != 12) L.ldh += 4;
-  int o = 0;
-  L.off_U = o; o += L.dk * L.ldu;
-  L.off_V = o; o += d * L.ldu;
-  L.off_H = o; o += d * L.ldh;
-  L.off_vec = o; o += 12 * ((d + 1) & ~1);   // Hessian diagonals of 4 stages (double buffered), sgt/2, isgt/2, sgi, isgi
-  L.total = (o + 1) & ~1;
-  return L;
-}
-
-constexpr int CHUNK_THREADS = 128;
-constexpr int CHUNK_WN = 5;   // n-tiles per warp: 2 nb <= 40
 
 // (q, p, S) of the separable model for K time steps, one warp per trajectory (lane owns the modes lane, lane+32):
 // classical RK4 on (q, p) (propagators.py:114-119, 361-368), the four Hessian diagonals of every step for the
@@ -147,280 +119,6 @@ k_qp_path(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double *
   if (lane == 0) rec[2 * d] = S;
 }
 
-// RK4 bookkeeping of one stage for the C-fragment elements of one warp (WM x WN tiles): kv = -acc, stage operand
-// formed in place (see the header).  S: stage 1..4 (compile time: straight-line code, loads batched per tile row).
-template <int S, int WM, int WN>
-__device__ __forceinline__ void chunk_phase_b(double *__restrict__ U, double *__restrict__ V, int ldu, int nb2, int d, int m0,
-                                              int fr, int fc, const double (&ima2)[WM], double h,
-                                              const double (&acc)[WM][WN][2], double (&R1)[WM][WN][2],
-                                              double (&R2)[WM][WN][2]) {
-  const double hh4 = 0.25 * h * h, hh2 = 0.5 * h * h, hh6 = h * h / 6.0, h2 = 0.5 * h, h6 = h / 6.0;
-#pragma unroll
-  for (int i = 0; i < WM; ++i) {
-    const int a = m0 + 8 * i + fr;
-    if (a < d) {
-      const double ima = ima2[i];
-      const int sw = swz(a);
-      double2 *urow = reinterpret_cast<double2 *>(U + a * ldu);
-      double2 *vrow = reinterpret_cast<double2 *>(V + a * ldu);
-      double2 u[WN], v[WN];
-#pragma unroll
-      for (int j = 0; j < WN; ++j) {
-        const int lc = 8 * j + 2 * fc;
-        u[j] = v[j] = make_double2(0.0, 0.0);
-        if (lc < nb2) {
-          u[j] = urow[(lc ^ sw) >> 1];
-          if (S != 2) v[j] = vrow[lc >> 1];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < WN; ++j) {
-        const int lc = 8 * j + 2 * fc;
-        if (lc < nb2) {
-          const double k0 = -acc[i][j][0], k1 = -acc[i][j][1];
-          if (S == 1) {
-            R1[i][j][0] = k0; R1[i][j][1] = k1;
-            u[j].x = fma(h2 * ima, v[j].x, u[j].x);
-            u[j].y = fma(h2 * ima, v[j].y, u[j].y);
-          } else if (S == 2) {
-            R2[i][j][0] = k0; R2[i][j][1] = k1;
-            u[j].x = fma(hh4 * ima, R1[i][j][0], u[j].x);
-            u[j].y = fma(hh4 * ima, R1[i][j][1], u[j].y);
-          } else if (S == 3) {
-            const double a1x = R1[i][j][0], a1y = R1[i][j][1], a2x = R2[i][j][0], a2y = R2[i][j][1];
-            u[j].x += (h2 * v[j].x + hh2 * a2x - hh4 * a1x) * ima;
-            u[j].y += (h2 * v[j].y + hh2 * a2y - hh4 * a1y) * ima;
-            R1[i][j][0] = hh6 * (a1x + a2x + k0) - hh2 * a2x;
-            R1[i][j][1] = hh6 * (a1y + a2y + k1) - hh2 * a2y;
-            R2[i][j][0] = a1x + 2.0 * a2x + 2.0 * k0;
-            R2[i][j][1] = a1y + 2.0 * a2y + 2.0 * k1;
-          } else {
-            u[j].x = fma(R1[i][j][0], ima, u[j].x);
-            u[j].y = fma(R1[i][j][1], ima, u[j].y);
-            v[j].x = fma(h6, R2[i][j][0] + k0, v[j].x);
-            v[j].y = fma(h6, R2[i][j][1] + k1, v[j].y);
-            vrow[lc >> 1] = v[j];
-          }
-          urow[(lc ^ sw) >> 1] = u[j];
-        }
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(CHUNK_THREADS, 3)
-k_rk4_chunk(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
-            const double *__restrict__ hd, ChunkLayout L) {
-  constexpr int WM = 2, WN = CHUNK_WN, TPT = CHUNK_THREADS;
-  extern __shared__ __align__(16) double smem[];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int d = E.d, ldu = L.ldu, ldh = L.ldh, nb = L.nb, nc = L.nc, DK = L.dk, dp = (d + 1) & ~1;
-  double *__restrict__ U = smem + L.off_U;
-  double *__restrict__ V = smem + L.off_V;
-  double *__restrict__ H = smem + L.off_H;
-  double *vec = smem + L.off_vec;
-  double *hdv = vec;                                   // [2][4][dp] Hessian diagonals, double buffered over steps
-  double *csa = vec + 8 * dp, *cisa = vec + 9 * dp, *csb = vec + 10 * dp, *cisb = vec + 11 * dp;
-  const int m0 = warp * WM * 8;
-  const int fr = lane >> 2, fc = lane & 3;
-  int bcol[WN];
-#pragma unroll
-  for (int j = 0; j < WN; ++j) bcol[j] = ((8 * j < 2 * nb) ? (8 * j + fr) : 0) ^ swz(fc);
-  double ima2[WM];
-#pragma unroll
-  for (int i = 0; i < WM; ++i) ima2[i] = (m0 + 8 * i + fr < d) ? P.imass[m0 + 8 * i + fr] : 0.0;
-
-  for (int i = t; i < d * ldh; i += TPT) H[i] = 0.0;
-  if (t < d) {
-    csa[t] = 0.5 * E.sgt[t];
-    cisa[t] = 0.5 * E.isgt[t];
-    csb[t] = E.sgi[t];
-    cisb[t] = E.isgi[t];
-  }
-  PT_DECL
-  const int nitems = ntb * nc;
-  const int nhd = 4 * dp;                              // doubles per (step, trajectory) row of hd
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int tl = item / nc, chunk = item - tl * nc;
-    const int traj = traj0 + tl;
-    const int b0 = chunk * nb;
-    const int nbc = (d - b0 < nb) ? d - b0 : nb;            // columns b of this chunk
-    double *rec = E.rec + (size_t)traj * E.rs;
-    __syncthreads();
-    for (int idx = t; idx < DK * ldu; idx += TPT) U[idx] = 0.0;
-    for (int idx = t; idx < d * ldu; idx += TPT) V[idx] = 0.0;
-    for (int i = t; i < nhd; i += TPT) hdv[i] = hd[((size_t)0 * ntb + tl) * nhd + i];
-    __syncthreads();
-    // local column lc < nb: (Mqq, Mpq)[:, b0+lc];  lc >= nb: (Mqp, Mpp)[:, b0+lc-nb]; 8 loads in flight per thread
-    {
-      const int ntot = d * 2 * nbc;
-      for (int base = 0; base < ntot; base += 8 * TPT) {
-        double uv[8], vv[8];
-        int la[8], lcs[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int idx = base + k * TPT + t;
-          uv[k] = vv[k] = 0.0;
-          la[k] = -1;
-          if (idx < ntot) {
-            const int a = idx / (2 * nbc), r = idx - a * 2 * nbc;
-            const int half = r / nbc, lb = r - half * nbc;
-            const int gcol = half * d + b0 + lb;
-            la[k] = a;
-            lcs[k] = half * nb + lb;
-            uv[k] = rec[E.qps + a * 2 * d + gcol];
-            vv[k] = rec[E.qps + 2 * d * d + a * 2 * d + gcol];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (la[k] >= 0) {
-            U[la[k] * ldu + (lcs[k] ^ swz(la[k]))] = uv[k];
-            V[la[k] * ldu + lcs[k]] = vv[k];
-          }
-      }
-    }
-    if (t < d) H[t * ldh + t] = hdv[t];
-    __syncthreads();
-    PT(0);
-
-    for (int step = 0; step < nsteps; ++step) {
-      const double *hcur = hdv + (step & 1) * nhd;
-      // prefetch the Hessian diagonals of the next step (consumed after the last barrier of this step)
-      double pre[2] = {0.0, 0.0};
-      const bool has_next = step + 1 < nsteps;
-      if (has_next) {
-        const double *src = hd + ((size_t)(step + 1) * ntb + tl) * nhd;
-        if (t < nhd) pre[0] = src[t];
-        if (t + TPT < nhd) pre[1] = src[t + TPT];
-      }
-      double R1[WM][WN][2], R2[WM][WN][2];
-#pragma unroll 1
-      for (int s = 1; s <= 4; ++s) {
-        // ---- phase A: acc = H_s U_s on the tensor pipe (software-pipelined fragment loads)
-        double acc[WM][WN][2];
-#pragma unroll
-        for (int i = 0; i < WM; ++i)
-#pragma unroll
-          for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        {
-          const int r0 = m0 + fr, r1 = m0 + 8 + fr;
-          const double *Ha0 = H + (r0 < d ? r0 : 0) * ldh + fc, *Ha1 = H + (r1 < d ? r1 : 0) * ldh + fc;
-          const bool v0 = r0 < d, v1 = r1 < d;
-          const double *Bp = U + fc * ldu;
-          const int ldu4 = 4 * ldu;
-          double a0 = v0 ? Ha0[0] : 0.0, a1 = v1 ? Ha1[0] : 0.0, b[WN];
-#pragma unroll
-          for (int j = 0; j < WN; ++j) b[j] = Bp[bcol[j]];
-          const int nk = DK >> 2;
-#pragma unroll 5
-          for (int k = 1; k <= nk; ++k) {
-            double an0 = 0.0, an1 = 0.0, bn[WN];
-            if (k < nk) {
-              Ha0 += 4;
-              Ha1 += 4;
-              Bp += ldu4;
-              an0 = v0 ? Ha0[0] : 0.0;
-              an1 = v1 ? Ha1[0] : 0.0;
-#pragma unroll
-              for (int j = 0; j < WN; ++j) bn[j] = Bp[bcol[j]];
-            }
-#pragma unroll
-            for (int j = 0; j < WN; ++j) {
-              dmma884(acc[0][j][0], acc[0][j][1], a0, b[j]);
-              dmma884(acc[1][j][0], acc[1][j][1], a1, b[j]);
-            }
-            a0 = an0;
-            a1 = an1;
-#pragma unroll
-            for (int j = 0; j < WN; ++j) b[j] = bn[j];
-          }
-        }
-        __syncthreads();
-        PT(2);
-        // ---- phase B: RK4 bookkeeping, next stage operand in place
-        if (s == 1) chunk_phase_b<1, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
-        else if (s == 2) chunk_phase_b<2, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
-        else if (s == 3) chunk_phase_b<3, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
-        else chunk_phase_b<4, WM, WN>(U, V, ldu, 2 * nb, d, m0, fr, fc, ima2, h, acc, R1, R2);
-        if (t < d && s < 4) H[t * ldh + t] = hcur[s * dp + t];
-        if (s == 4 && has_next) {
-          double *hn = hdv + ((step + 1) & 1) * nhd;
-          if (t < nhd) hn[t] = pre[0];
-          if (t + TPT < nhd) hn[t + TPT] = pre[1];
-          if (t < d) H[t * ldh + t] = pre[0];          // stage 1 of the next step (row 0 of the next buffer)
-        }
-        __syncthreads();
-        PT(3);
-      }
-      // ---- this chunk's columns of the prefactor matrix (propagators.py:969-986 with diagonal width matrices)
-      {
-        double2 *out = cm + ((size_t)step * ntb + tl) * d * d;
-        for (int idx = t; idx < d * nbc; idx += TPT) {
-          const int a = idx / nbc, lb = idx - a * nbc, b = b0 + lb;
-          const int sw = swz(a);
-          const double mqq = U[a * ldu + (lb ^ sw)], mqp = U[a * ldu + ((nb + lb) ^ sw)];
-          const double mpq = V[a * ldu + lb], mpp = V[a * ldu + nb + lb];
-          const double sa = csa[a], isa = cisa[a], sb = csb[b], isb = cisb[b];
-          out[a * d + b] = make_double2(sa * mqq * isb + isa * mpp * sb, -sa * mqp * sb + isa * mpq * isb);
-        }
-      }
-      PT(4);
-    }
-    // ---- write back
-    __syncthreads();
-    for (int idx = t; idx < d * 2 * nbc; idx += TPT) {
-      const int a = idx / (2 * nbc), r = idx - a * 2 * nbc;
-      const int half = r / nbc, lb = r - half * nbc;
-      const int lc = half * nb + lb, gcol = half * d + b0 + lb;
-      rec[E.qps + a * 2 * d + gcol] = U[a * ldu + (lc ^ swz(a))];
-      rec[E.qps + 2 * d * d + a * 2 * d + gcol] = V[a * ldu + lc];
-    }
-    PT(8);
-  }
-}
-
-// ------------------------------------------------------------------ warp-private column tiles -------------
-// Second formulation of the chunk kernel.  Warp j of the CTA owns tile j of the chunk: the 4 columns
-// b = b0 + 4j .. b0 + 4j + 3 of BOTH halves, interleaved as local columns (2 lb, 2 lb + 1) = (q-half, p-half), and ALL
-// rows.  Then
-//   * the B operand of H U_s (an 8-column slab of U_s) and the elements the warp updates in phase B are the same
-//     warp-private 60 x 8 slab: MMA and bookkeeping are separated by __syncwarp, never by a CTA barrier
-//   * each thread ends up with (Mqq, Mqp, Mpq, Mpp)[a][b] of its elements in registers after stage 4: the
-//     prefactor-matrix column is assembled without touching shared memory
-//   * the Hessian is held as H_s = H0 + diag(h_s): the dense base H0 (shared memory, zero off-diagonal part of the
-//     separable model, loaded once) is multiplied in full on the tensor pipe, the stage-dependent diagonal is
-//     added to the A fragment of the diagonal tile (one predicated add per k-step).  No per-stage rewrite of H, so
-//     the warps of a CTA drift freely inside a time step; ONE CTA barrier per step swaps the double-buffered
-//     Hessian diagonals.
-// Layout of a slab in shared memory: row-major [row][8]; B-fragment loads (4 rows x 8 columns = 256 contiguous
-// bytes) and the 128-bit owner accesses (8 rows x 64 bytes) are conflict free without swizzling.
-__host__ __device__ constexpr int cols_ldh(int nk);
-struct ColsLayout {
-  int nc, nb, ntile, ldh, dk;
-  int off_H, off_T, off_hd, off_c, slab, total;   // doubles
-};
-
-__host__ __device__ inline ColsLayout make_cols_layout(int d) {
-  ColsLayout L;
-  // 4 warps per CTA (one per SM sub-partition: warps are bound to schedulers by warp index mod 4, so any other
-  // count leaves the FP64 pipes of the sub-partitions unevenly loaded), 4 columns b per warp
-  L.nb = 16;
-  L.nc = (d + L.nb - 1) / L.nb;
-  L.ntile = 4;
-  L.dk = (d + 3) & ~3;
-  L.ldh = cols_ldh(L.dk / 4);
-  const int dp = (d + 1) & ~1;
-  int o = 0;
-  L.off_H = o; o += d * L.ldh;
-  L.slab = (L.dk + d) * 8;                 // U slab (dk rows, zero padded) + V slab (d rows)
-  L.off_T = o; o += L.ntile * L.slab;
-  L.off_hd = o; o += 2 * 4 * dp;
-  L.off_c = o; o += 4 * dp;
-  L.total = (o + 1) & ~1;
-  return L;
-}
-
 template <int S>
 __device__ __forceinline__ void cols_phase_b(double2 &u, double2 &v, double ima, double h, double k0, double k1, double (&R1)[2],
                                              double (&R2)[2]) {
@@ -451,182 +149,6 @@ __device__ __forceinline__ void cols_phase_b(double2 &u, double2 &v, double ima,
 
 // leading dimension of the Hessian base for NK k-steps: >= 4 NK with ld mod 16 in {4, 12} (conflict-free A fragments)
 __host__ __device__ constexpr int cols_ldh(int nk) { return (4 * nk) % 16 == 4 || (4 * nk) % 16 == 12 ? 4 * nk : ((4 * nk + 4) % 16 == 4 || (4 * nk + 4) % 16 == 12 ? 4 * nk + 4 : 4 * nk + 8); }
-
-// NK = number of k-steps (dk / 4): compile time, so that every fragment load has an immediate offset and the
-// diagonal tile of each k-step is static.  The stage loop is NOT unrolled (one copy of the MMA code).
-template <int NK>
-__global__ void __launch_bounds__(128, 3)
-k_rk4_cols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
-           const double *__restrict__ hd, ColsLayout L) {
-  constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
-  constexpr int LDH = cols_ldh(NK), DK = 4 * NK;
-  extern __shared__ __align__(16) double smem[];
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nthr = blockDim.x;
-  const int d = E.d, nb = L.nb, nc = L.nc, dp = (d + 1) & ~1;
-  double *__restrict__ Us = smem + L.off_T + warp * L.slab;
-  double *__restrict__ Vs = Us + DK * 8;
-  double *hdv = smem + L.off_hd;                      // [2][4][dp]
-  const double *csa = smem + L.off_c, *cisa = csa + dp, *csb = cisa + dp, *cisb = csb + dp;
-  const int fr = lane >> 2, fc = lane & 3;
-  const bool pe = (fr == fc), po = (fr == fc + 4);    // lanes holding a diagonal element in even / odd k-steps
-  const bool last_ok = (8 * (MT - 1) + fr) < d;       // only the last row tile can stick out of the matrix
-  const double *__restrict__ Hfr = smem + L.off_H + (last_ok ? fr : 0) * LDH + fc;   // rows 8 i + fr (clamped in the last tile)
-  const double *__restrict__ Hfr0 = smem + L.off_H + fr * LDH + fc;
-  const double *__restrict__ Ub = Us + fc * 8 + fr;
-  double2 *__restrict__ Uo = reinterpret_cast<double2 *>(Us + fr * 8 + 2 * fc);
-  double2 *__restrict__ Vo = reinterpret_cast<double2 *>(Vs + fr * 8 + 2 * fc);
-  double ima[MT];
-#pragma unroll
-  for (int i = 0; i < MT; ++i) ima[i] = (8 * i + fr < d) ? P.imass[8 * i + fr] : 0.0;
-
-  // dense base of the Hessian: off-diagonal part (identically zero for the separable models served here)
-  for (int i = t; i < d * LDH; i += nthr) smem[L.off_H + i] = 0.0;
-  if (t < d) {
-    double *c = smem + L.off_c;
-    c[t] = 0.5 * E.sgt[t];
-    c[dp + t] = 0.5 * E.isgt[t];
-    c[2 * dp + t] = E.sgi[t];
-    c[3 * dp + t] = E.isgi[t];
-  }
-  const int nitems = ntb * nc;
-  const int nhd = 4 * dp;
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const int tl = item / nc, chunk = item - tl * nc;
-    const int traj = traj0 + tl;
-    const int b0 = chunk * nb;
-    const int bend = (b0 + nb < d) ? b0 + nb : d;
-    const int b = b0 + 4 * warp + fc;                       // the column b this thread's elements belong to
-    const bool bok = b < bend;
-    const bool tile_ok = b0 + 4 * warp < bend;              // warp uniform: this warp's tile holds at least one column
-    double *rec = E.rec + (size_t)traj * E.rs;
-    __syncthreads();                                        // everybody is done with the previous item
-    for (int i = t; i < nhd; i += nthr) hdv[i] = hd[(size_t)tl * nhd + i];
-    // ---- load the slab: row a = 8 i + fr, element pair (2 fc, 2 fc + 1) = (q-half, p-half) of column b
-    {
-      double2 u[MT], v[MT];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int a = 8 * i + fr;
-        u[i] = v[i] = make_double2(0.0, 0.0);
-        if (a < d && bok) {
-          const double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
-          u[i] = make_double2(ru[b], ru[d + b]);
-          v[i] = make_double2(rv[b], rv[d + b]);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int a = 8 * i + fr;
-        if (a < DK) Uo[i * 32] = u[i];
-        if (a < d) Vo[i * 32] = v[i];
-      }
-    }
-    __syncthreads();
-
-    for (int step = 0; step < nsteps; ++step) {
-      const double *hcur = hdv + (step & 1) * nhd;
-      double pre[2] = {0.0, 0.0};
-      const bool has_next = step + 1 < nsteps;
-      if (has_next) {
-        const double *src = hd + ((size_t)(step + 1) * ntb + tl) * nhd;
-        if (t < nhd) pre[0] = src[t];
-        if (t + nthr < nhd) pre[1] = src[t + nthr];
-      }
-      double R1[MT][2], R2[MT][2];
-      double2 *out = cm + ((size_t)step * ntb + tl) * d * d + (size_t)fr * d + (bok ? b : 0);
-      const double sb = bok ? csb[b] : 0.0, isb = bok ? cisb[b] : 0.0;
-#pragma unroll 1
-      for (int s = 1; s <= (tile_ok ? 4 : 0); ++s) {
-        const double *__restrict__ hsf = hcur + (s - 1) * dp + fr;
-        // ---- H_s U_s on the tensor pipe: 8-row tiles x this warp's 8 columns
-        double acc[MT][2];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = 0.0;
-#pragma unroll
-        for (int kk = 0; kk < NK; ++kk) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const double bf = Ub[kk * 32];
-          double af[MT];
-#pragma unroll
-          for (int i = 0; i < MT - 1; ++i) af[i] = Hfr0[i * 8 * LDH + 4 * kk];
-          af[MT - 1] = last_ok ? Hfr[(MT - 1) * 8 * LDH + 4 * kk] : 0.0;
-          {
-            const int id = kk >> 1;                          // tile that contains the diagonal of this k-step
-            const bool on = ((kk & 1) ? po : pe) && (id < MT - 1 || last_ok);
-            const double hv = hsf[(8 * id < 8 * (MT - 1) || last_ok) ? 8 * id : 0];
-            if (on) af[id] += hv;
-          }
-#pragma unroll
-          for (int i = 0; i < MT; ++i) dmma884(acc[i][0], acc[i][1], af[i], bf);
-        }
-        __syncwarp();
-        // ---- RK4 bookkeeping on the warp's own slab, stage operand in place
-        if (s == 1) {
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<1>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else if (s == 2) {
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = make_double2(0.0, 0.0);
-              cols_phase_b<2>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else if (s == 3) {
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<3>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-            }
-        } else {
-#pragma unroll
-          for (int i = 0; i < MT; ++i)
-            if (i < MT - 1 || last_ok) {
-              double2 u = Uo[i * 32], v = Vo[i * 32];
-              cols_phase_b<4>(u, v, ima[i], h, -acc[i][0], -acc[i][1], R1[i], R2[i]);
-              Uo[i * 32] = u;
-              Vo[i * 32] = v;
-              // prefactor-matrix element (propagators.py:969-986, diagonal width matrices) straight from registers:
-              // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
-              if (bok) {
-                const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
-                out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
-              }
-            }
-        }
-        __syncwarp();
-      }
-      // ---- Hessian diagonals of the next step into the other buffer; one CTA barrier per time step
-      if (has_next) {
-        double *hn = hdv + ((step + 1) & 1) * nhd;
-        if (t < nhd) hn[t] = pre[0];
-        if (t + nthr < nhd) hn[t + nthr] = pre[1];
-      }
-      __syncthreads();
-    }
-    // ---- write back
-    if (bok) {
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int a = 8 * i + fr;
-        if (a < d) {
-          const double2 u = Uo[i * 32], v = Vo[i * 32];
-          double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
-          ru[b] = u.x; ru[d + b] = u.y;
-          rv[b] = v.x; rv[d + b] = v.y;
-        }
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------ warp-independent variant ----------------
 // Same arithmetic as k_rk4_cols with the work item shrunk to (trajectory, ONE tile of 4 columns b) and owned by a
@@ -894,36 +416,6 @@ static cudaError_t launch_wcols(int grid, const EngDev &E, const PotDev &P, doub
   }
 }
 
-static bool cols_supported(const EngDev &E, const PotDev &P) {
-  if (!E.diag || E.dr != E.d) return false;
-  if (P.type != POT_MORSE && P.type != POT_NONHARMONIC) return false;
-  if (E.d <= 32 || E.d > 64) return false;
-  const ColsLayout L = make_cols_layout(E.d);
-  return L.ntile <= 5;
-}
-
-template <int NK>
-static cudaError_t launch_cols_t(int grid, int threads, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps,
-                                 int traj0, int ntb, double2 *cm, const double *hd, const ColsLayout &L, cudaStream_t st) {
-  cudaError_t ce = cudaFuncSetAttribute(k_rk4_cols<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (ce != cudaSuccess) return ce;
-  k_rk4_cols<NK><<<grid, threads, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
-  return cudaGetLastError();
-}
-
-static cudaError_t launch_cols(int grid, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb, double2 *cm,
-                               const double *hd, const ColsLayout &L, cudaStream_t st) {
-  const size_t smem = sizeof(double) * (size_t)L.total;
-  const int threads = 32 * L.ntile;
-  switch (L.dk / 4) {
-#define SC_COLS_CASE(N) case N: return launch_cols_t<N>(grid, threads, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st);
-    SC_COLS_CASE(9) SC_COLS_CASE(10) SC_COLS_CASE(11) SC_COLS_CASE(12) SC_COLS_CASE(13) SC_COLS_CASE(14) SC_COLS_CASE(15)
-    SC_COLS_CASE(16)
-#undef SC_COLS_CASE
-    default: return cudaErrorInvalidValue;
-  }
-}
-
 // one thread per trajectory of the batch, time steps in order; partials: (gridDim.x, nsteps_total, 5) rows of this
 // batch's blocks (row stride nsteps_total, first step of this launch = step0)
 __global__ void __launch_bounds__(128)
@@ -973,9 +465,7 @@ k_hk_finish(EngDev E, int traj0, int ntb, int nsteps, int step0, int nsteps_tota
 static bool chunk_supported(const EngDev &E, const PotDev &P) {
   if (!E.diag || E.dr != E.d) return false;
   if (P.type != POT_MORSE && P.type != POT_NONHARMONIC) return false;
-  if (E.d <= 32 || E.d > 62) return false;
-  const ChunkLayout L = make_chunk_layout(E.d);
-  return 2 * L.nb <= 8 * CHUNK_WN && E.d <= 64;
+  return E.d > 32 && E.d <= 64;
 }
 
 }  // namespace sc

@@ -103,8 +103,6 @@ struct sc_engine {
   void *chunk_scratch = nullptr;   // prefactor matrices, determinants, aux rows of one batch (chunked path)
   size_t chunk_scratch_cap = 0;
   // optional per-kernel timing of the chunked path (CUDA events on the launching stream)
-  cudaStream_t s2 = nullptr;       // second stream of the chunked pipeline (LU / finish side)
-  cudaEvent_t ev_rk4[2] = {nullptr, nullptr}, ev_lu[2] = {nullptr, nullptr}, ev_join = nullptr;
   bool timing = false;
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -124,12 +122,6 @@ struct sc_engine {
     if (corr_dev) cudaFree(corr_dev);
     if (chunk_scratch) cudaFree(chunk_scratch);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
-    for (int i = 0; i < 2; ++i) {
-      if (ev_rk4[i]) cudaEventDestroy(ev_rk4[i]);
-      if (ev_lu[i]) cudaEventDestroy(ev_lu[i]);
-    }
-    if (ev_join) cudaEventDestroy(ev_join);
-    if (s2) cudaStreamDestroy(s2);
   }
 };
 
@@ -544,18 +536,15 @@ static int ensure_partials(sc_engine *e, size_t need, cudaStream_t st) {
   return SC_OK;
 }
 
-// column-chunked path (sc_chunk.cuh): RK4/monodromy kernel -> batched LU -> branch tracking + contributions,
-// batch by batch over the ensemble, KC time steps per launch
+// column pipeline (sc_chunk.cuh): (q,p) path kernel -> RK4/monodromy kernel -> batched LU -> branch tracking +
+// contributions, window by window over the ensemble, KC time steps per pass.  (Running the LU of window i next to
+// the RK4 kernel of window i + 1 on a second stream was measured 20 % slower: the LU's pivot chain shares the FP64
+// pipe with the DMMA stream.)
 static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
   const int d = e->dev.d, n = e->dev.n, sm = e->sm_count;
-  const ChunkLayout L = make_chunk_layout(d);
-  const ColsLayout LC = make_cols_layout(d);
-  const bool use_cols = cols_supported(e->dev, P) && !getenv("SC_NO_COLS");
   int wcols_tiles = 1;                                  // column tiles per warp of k_rk4_wcols (2: measured slower, 8 warps / SM)
   if (const char *s = getenv("SC_WCOLS_TILES")) wcols_tiles = atoi(s) == 2 ? 2 : 1;
   const WColsLayout LW = make_wcols_layout(d, wcols_tiles);
-  const bool use_wcols = use_cols && !getenv("SC_NO_WCOLS");
-  const size_t smem = sizeof(double) * (size_t)L.total;
   // time steps per pass over the state: the records are read and written once per pass, so longer passes amortise the
   // state traffic and the pipeline fill (K = 8 -> 10 -> 20: +2.3 %, +4 %); passes of a launch are balanced
   int KC = 20;
@@ -564,120 +553,71 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
     const int npass = (nsteps + KC - 1) / KC;
     KC = (nsteps + npass - 1) / npass;
   }
-  // Two-stream software pipeline: the RK4 kernel of batch i+1 (FP64 tensor pipe bound) runs concurrently with the LU
-  // kernel of batch i (latency / issue bound) on the SAME SMs -- 2 RK4 CTAs + 1 LU CTA fit in the shared memory and
-  // the register file of an SM -- with double-buffered scratch.  SC_CHUNK_OVERLAP=0 serialises the kernels.
-  bool overlap = false;
-  if (const char *s = getenv("SC_CHUNK_OVERLAP")) overlap = atoi(s) != 0;
-  const int nbuf = overlap ? 2 : 1;
   const int dp = (d + 1) & ~1;
   const size_t per_traj = (size_t)KC * ((size_t)d * d * sizeof(double2) + sizeof(double2) + 8 * sizeof(double) + 4 * dp * sizeof(double));
   size_t budget = (size_t)3 << 30;
   if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
-  long long ntb = (long long)(budget / nbuf / per_traj);
+  long long ntb = (long long)(budget / per_traj);
   ntb = (ntb / sm) * sm;
   if (ntb < sm) ntb = sm;
   if (ntb > n) ntb = n;
-  const size_t buf_bytes = (per_traj * (size_t)ntb + 255) & ~(size_t)255;
-  const size_t need_bytes = buf_bytes * nbuf;
+  const size_t need_bytes = per_traj * (size_t)ntb + 512;
   if (need_bytes > e->chunk_scratch_cap) {
     CU(cudaStreamSynchronize(st));
     if (e->chunk_scratch) cudaFree(e->chunk_scratch);
     e->chunk_scratch = nullptr;
-    // sized for the largest step count per launch so that a later call with another K does not reallocate
+    // sized for the largest step count per pass so that a later call with another K does not reallocate
     const size_t per20 = per_traj / KC * 20;
-    size_t want = std::max(need_bytes, std::min(budget, per20 * (size_t)n * nbuf) + 512);
+    size_t want = std::max(need_bytes, std::min(budget, per20 * (size_t)n) + 512);
     CU(cudaMalloc(&e->chunk_scratch, want));
     e->chunk_scratch_cap = want;
   }
-  if (overlap && !e->s2) {
-    CU(cudaStreamCreateWithFlags(&e->s2, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CU(cudaEventCreateWithFlags(&e->ev_rk4[i], cudaEventDisableTiming));
-      CU(cudaEventCreateWithFlags(&e->ev_lu[i], cudaEventDisableTiming));
-    }
-    CU(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t s2 = overlap ? e->s2 : st;
+  double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
+  double2 *det = cm + (size_t)KC * ntb * d * d;
+  double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
+  double *hd = aux + (size_t)KC * ntb * 8;
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
-  CU(cudaFuncSetAttribute(k_rk4_chunk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  long long rk4_per_sm = 3, lu_per_sm = 0;   // 0: the LU launcher's default occupancy
+  long long rk4_per_sm = LW.ntw == 2 ? 2 : 3, lu_per_sm = 0;   // 0: the LU launcher's default occupancy
   if (const char *s = getenv("SC_CHUNK_CTAS")) rk4_per_sm = atoi(s) > 0 ? atoi(s) : rk4_per_sm;
   if (const char *s = getenv("SC_LU_CTAS")) lu_per_sm = atoi(s) > 0 ? atoi(s) : lu_per_sm;
-  auto mark = [&](cudaStream_t stream) {
+  auto mark = [&]() {                       // per-kernel timing (sc_engine_set_timing): 5 events per window
     if (!e->timing) return;
     if (e->tev_used == e->tev.size()) {
       cudaEvent_t ev;
       cudaEventCreate(&ev);
       e->tev.push_back(ev);
     }
-    cudaEventRecord(e->tev[e->tev_used++], stream);
+    cudaEventRecord(e->tev[e->tev_used++], st);
   };
-  if (overlap) {
-    // the second stream starts after everything already queued on the caller's stream
-    CU(cudaEventRecord(e->ev_join, st));
-    CU(cudaStreamWaitEvent(s2, e->ev_join, 0));
-  }
-  long long seq = 0;
   for (int s0 = 0; s0 < nsteps; s0 += KC) {
     const int ks = std::min(KC, nsteps - s0);
     size_t g0 = 0;
-    for (long long t0 = 0; t0 < n; t0 += ntb, ++seq) {
+    for (long long t0 = 0; t0 < n; t0 += ntb) {
       const int nt = (int)std::min<long long>(ntb, n - t0);
-      const int buf = (int)(seq % nbuf);
-      unsigned char *base = reinterpret_cast<unsigned char *>(e->chunk_scratch) + buf_bytes * buf;
-      double2 *cm = reinterpret_cast<double2 *>(base);
-      double2 *det = cm + (size_t)KC * ntb * d * d;
-      double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
-      double *hd = aux + (size_t)KC * ntb * 8;
-      long long grid = (long long)nt * (use_cols ? LC.nc : L.nc);
-      if (use_wcols) {
-        grid = ((long long)nt * LW.nitem + 3) / 4;
-        if (!getenv("SC_CHUNK_CTAS")) rk4_per_sm = LW.ntw == 2 ? 2 : 3;
-      }
+      long long grid = ((long long)nt * LW.nitem + 3) / 4;
       if (grid > rk4_per_sm * sm) grid = rk4_per_sm * sm;
-      // producer side (caller's stream): this scratch buffer must have been consumed (two batches ago)
-      if (overlap && seq >= nbuf) CU(cudaStreamWaitEvent(st, e->ev_lu[buf], 0));
-      mark(st);
+      mark();
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
-      mark(st);
-      if (use_wcols) {
-        CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, st));
-      } else if (use_cols) {
-        CU(launch_cols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LC, st));
-      } else {
-        k_rk4_chunk<<<(int)grid, CHUNK_THREADS, smem, st>>>(e->dev, P, h, ks, (int)t0, nt, cm, hd, L);
-        CU(cudaGetLastError());
-      }
-      mark(st);
-      // consumer side (second stream): determinants, branch tracking, contributions
-      if (overlap) {
-        CU(cudaEventRecord(e->ev_rk4[buf], st));
-        CU(cudaStreamWaitEvent(s2, e->ev_rk4[buf], 0));
-      }
-      mark(s2);
-      CU(launch_lu_batch(cm, d, ks * nt, det, sm, (int)lu_per_sm, s2));
-      mark(s2);
+      mark();
+      CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, st));
+      mark();
+      CU(launch_lu_batch(cm, d, ks * nt, det, sm, (int)lu_per_sm, st));
+      mark();
       const int nblk = (nt + 127) / 128;
-      k_hk_finish<<<nblk, 128, 0, s2>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
+      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
       CU(cudaGetLastError());
-      mark(s2);
-      if (overlap) CU(cudaEventRecord(e->ev_lu[buf], s2));
+      mark();
       g0 += nblk;
       e->launches += 4;
     }
   }
-  if (overlap) {
-    CU(cudaEventRecord(e->ev_join, s2));
-    CU(cudaStreamWaitEvent(st, e->ev_join, 0));
-  }
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
   e->launches += 1;
-  e->kernel_name = use_wcols ? "k_rk4_wcols+k_lu_mma+k_hk_finish" : (use_cols ? "k_rk4_cols+k_lu_mma+k_hk_finish" : "k_rk4_chunk+k_lu_mma+k_hk_finish");
+  e->kernel_name = "k_rk4_wcols+k_lu_mma+k_hk_finish";
   return SC_OK;
 }
 
@@ -1102,17 +1042,13 @@ extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
   if (e->tev_used) {
     CU(cudaEventSynchronize(e->tev[e->tev_used - 1]));
     CU(cudaDeviceSynchronize());
-    // per batch: [before qp_path, after qp_path, after rk4] on the producer stream, [before lu, after lu, after finish] on the consumer
-    for (size_t i = 0; i + 5 < e->tev_used; i += 6) {
-      float ms = 0.0f;
-      CU(cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]));
-      e->tms[0] += ms;
-      CU(cudaEventElapsedTime(&ms, e->tev[i + 1], e->tev[i + 2]));
-      e->tms[1] += ms;
-      CU(cudaEventElapsedTime(&ms, e->tev[i + 3], e->tev[i + 4]));
-      e->tms[2] += ms;
-      CU(cudaEventElapsedTime(&ms, e->tev[i + 4], e->tev[i + 5]));
-      e->tms[3] += ms;
+    // per window: 5 marks around k_qp_path, k_rk4_wcols, k_lu_mma, k_hk_finish
+    for (size_t i = 0; i + 4 < e->tev_used; i += 5) {
+      for (int k = 0; k < 4; ++k) {
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, e->tev[i + k], e->tev[i + k + 1]));
+        e->tms[k] += ms;
+      }
     }
     e->tev_used = 0;
   }

@@ -221,84 +221,6 @@ __device__ __forceinline__ void flow_wait(int *flag, int want) {
   } while (v < want);
 }
 
-// base: number of panels published by earlier matrices of this CTA (the counter is never reset); the caller
-// separates consecutive matrices by a CTA barrier (panel slots are reused).
-template <int NW, int NBLK>
-__device__ __forceinline__ double2 lu_det_flow(double2 (&lo)[NBLK][4], double2 (&hi)[NBLK][4], int dr, LuFlow *sh, int base,
-                                               int w, int lane) {
-  const bool use_hi = dr > 32;
-  const int nblocks = (dr + 3) >> 2;
-  unsigned long long done = 0ull;
-  if (w == 0) {
-    unsigned long long dn = 0ull;
-    lu_panel(lo[0], hi[0], min(4, dr), dn, use_hi, &sh->panel[0], lane);
-    __syncwarp();
-    if (lane == 0) flow_publish(&sh->ready, base + 1);
-  }
-  double2 det = make_double2(1.0, 0.0);
-  int inversions = 0;
-#pragma unroll
-  for (int s = 0; s < NBLK; ++s) {
-#pragma unroll 1
-    for (int ww = 0; ww < NW; ++ww) {
-      const int K = s * NW + ww;
-      if (K >= nblocks) break;
-      flow_wait(&sh->ready, base + K + 1);
-      const LuPanel *P = &sh->panel[K];
-      const int ncol = min(4, dr - 4 * K);
-      int p[4];
-      double2 flo[4], fhi[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        p[c] = P->p[c];
-        flo[c] = P->f[c][lane];
-        fhi[c] = P->f[c][lane + 32];
-        if (c < ncol) {
-          det = cmul(det, P->pv[c]);
-          inversions += __popcll(done >> p[c]);
-          done |= 1ull << p[c];
-        } else {
-          flo[c] = fhi[c] = make_double2(0.0, 0.0);
-          p[c] = 0;
-        }
-      }
-      if (K + 1 < nblocks) {
-        auto apply = [&](double2(&l)[4], double2(&h)[4]) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) lu_rank1(l[j], h[j], p[c], flo[c], fhi[c], use_hi);
-          }
-        };
-        const bool wrap = (ww + 1 == NW);
-        const int wn = wrap ? 0 : ww + 1;
-        if (w == wn) {
-          unsigned long long dn = done;
-          if (wrap) {
-            if (s + 1 < NBLK) {
-              apply(lo[s + 1 < NBLK ? s + 1 : s], hi[s + 1 < NBLK ? s + 1 : s]);
-              lu_panel(lo[s + 1 < NBLK ? s + 1 : s], hi[s + 1 < NBLK ? s + 1 : s], min(4, dr - 4 * (K + 1)), dn, use_hi,
-                       &sh->panel[K + 1], lane);
-            }
-          } else {
-            apply(lo[s], hi[s]);
-            lu_panel(lo[s], hi[s], min(4, dr - 4 * (K + 1)), dn, use_hi, &sh->panel[K + 1], lane);
-          }
-          __syncwarp();
-          if (lane == 0) flow_publish(&sh->ready, base + K + 2);
-        }
-        if (w > ww + 1) apply(lo[s], hi[s]);
-#pragma unroll
-        for (int s2 = s + 1; s2 < NBLK; ++s2) {
-          if (!(wrap && w == 0 && s2 == s + 1)) apply(lo[s2], hi[s2]);
-        }
-      }
-    }
-  }
-  if (inversions & 1) { det.x = -det.x; det.y = -det.y; }
-  return det;
-}
-
 // ------------------------------------------------------------------ left-looking dataflow variant ----------
 // Each warp brings ONE 4-column block at a time up to date: it applies the published panels 0..J-1 in order (waiting
 // on the release/acquire counter only when it is ahead of the factorisation front), factors its block in-warp and
@@ -363,151 +285,6 @@ __device__ __forceinline__ double2 lu_det_left(const double2 *__restrict__ A, in
         const int pk = sh->panel[k >> 2].p[k & 3];
         det = cmul(det, sh->panel[k >> 2].pv[k & 3]);
         for (int k2 = 0; k2 < k; ++k2) inv += (sh->panel[k2 >> 2].p[k2 & 3] > pk) ? 1 : 0;
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ox = __shfl_xor_sync(0xffffffffu, det.x, o), oy = __shfl_xor_sync(0xffffffffu, det.y, o);
-      det = cmul(det, make_double2(ox, oy));
-      inv += __shfl_xor_sync(0xffffffffu, inv, o);
-    }
-    if (inv & 1) { det.x = -det.x; det.y = -det.y; }
-  }
-  return det;
-}
-
-// ------------------------------------------------------------------ compact left-looking variant -----------
-// Same algorithm as lu_det_left with the multiplier columns stored only for the rows that are still active when
-// their panel starts (64 - 4K rows for panel K): 34 KB instead of 61 KB per matrix, so that SIX matrices per SM are
-// in flight (the factorisation is latency / issue bound: more independent matrices = more throughput).  A row's slot
-// inside panel K is its rank among the active rows, popc(active & ((1 << row) - 1)).
-struct LuFlowC {
-  double2 f[2176];                          // sum_K 4 (64 - 4K), K = 0..15
-  double2 pv[LU_MAX_PANELS][4];
-  int p[LU_MAX_PANELS][4];
-  unsigned long long bar[LU_MAX_PANELS];
-  int ready;
-  int pad[3];
-};
-__device__ __forceinline__ int luc_off(int K) { return 256 * K - 8 * K * (K - 1); }
-
-__device__ __forceinline__ void luc_bar_init(LuFlowC *sh, int t) {
-  if (t < LU_MAX_PANELS)
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(&sh->bar[t]))));
-  if (t == 0) sh->ready = 0;
-}
-
-// in-warp factorisation of panel K; done = rows retired before this panel
-__device__ __forceinline__ void luc_panel(double2 (&lo)[4], double2 (&hi)[4], int ncol, unsigned long long done, LuFlowC *sh,
-                                          int K, int lane) {
-  const unsigned long long act0 = ~done;
-  const int nact = 64 - 4 * K;
-  const bool s_lo = (act0 >> lane) & 1ull, s_hi = (act0 >> (lane + 32)) & 1ull;
-  const int pos_lo = __popcll(act0 & ((1ull << lane) - 1ull));
-  const int pos_hi = __popcll(act0 & ((1ull << (lane + 32)) - 1ull));
-  double2 *fb = sh->f + luc_off(K);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c < ncol) {
-      const double mlo = lo[c].x * lo[c].x + lo[c].y * lo[c].y, mhi = hi[c].x * hi[c].x + hi[c].y * hi[c].y;
-      unsigned key = 0u;
-      if (!((done >> lane) & 1ull)) key = lu_key2(mlo, lane);
-      if (!((done >> (lane + 32)) & 1ull)) key = max(key, lu_key2(mhi, lane + 32));
-      const double rlo = fast_rcp(mlo == 0.0 ? 1.0 : mlo), rhi = fast_rcp(mhi == 0.0 ? 1.0 : mhi);
-      const unsigned kk = __reduce_max_sync(0xffffffffu, key);
-      const int p = static_cast<int>(kk & 63u);
-      const bool ph = p >= 32;
-      double px = ph ? hi[c].x : lo[c].x, py = ph ? hi[c].y : lo[c].y;
-      const double rr = ph ? rhi : rlo;
-      double ix = px * rr, iy = -py * rr;
-      px = __shfl_sync(0xffffffffu, px, p & 31);
-      py = __shfl_sync(0xffffffffu, py, p & 31);
-      ix = __shfl_sync(0xffffffffu, ix, p & 31);
-      iy = __shfl_sync(0xffffffffu, iy, p & 31);
-      done |= 1ull << p;
-      double2 flo = make_double2(lo[c].x * ix - lo[c].y * iy, lo[c].x * iy + lo[c].y * ix);
-      double2 fhi = make_double2(hi[c].x * ix - hi[c].y * iy, hi[c].x * iy + hi[c].y * ix);
-      if ((done >> lane) & 1ull) flo = make_double2(0.0, 0.0);
-      if ((done >> (lane + 32)) & 1ull) fhi = make_double2(0.0, 0.0);
-#pragma unroll
-      for (int c2 = c + 1; c2 < 4; ++c2) lu_rank1(lo[c2], hi[c2], p, flo, fhi, true);
-      if (s_lo) fb[c * nact + pos_lo] = flo;
-      if (s_hi) fb[c * nact + pos_hi] = fhi;
-      if (lane == 0) {
-        sh->p[K][c] = p;
-        sh->pv[K][c] = make_double2(px, py);
-      }
-    } else if (lane == 0) {
-      sh->p[K][c] = 0;
-      sh->pv[K][c] = make_double2(1.0, 0.0);
-    }
-  }
-}
-
-// A: element (LU row r, LU column c) at A[c * ld + r]; 32 < dr <= 64.  Determinant on warp 0.
-template <int NW>
-__device__ __forceinline__ double2 luc_det_left(const double2 *__restrict__ A, int ld, int dr, LuFlowC *sh, int base,
-                                                unsigned parity, int w, int lane) {
-  const int nblocks = (dr + 3) >> 2;
-  int known = 0;
-  for (int J = w; J < nblocks; J += NW) {
-    double2 lo[4], hi[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col = 4 * J + c;
-      lo[c] = hi[c] = make_double2(0.0, 0.0);
-      if (col < dr) {
-        if (lane < dr) lo[c] = A[(size_t)col * ld + lane];
-        if (lane + 32 < dr) hi[c] = A[(size_t)col * ld + lane + 32];
-      }
-    }
-    unsigned long long done = 0ull;
-#pragma unroll 1
-    for (int K = 0; K < J; ++K) {
-      if (known <= K) {
-        known = flow_peek(&sh->ready) - base;
-        if (known <= K) {
-          flow_bar_wait(&sh->bar[K], parity);
-          known = K + 1;
-        }
-      }
-      const unsigned long long act0 = ~done;
-      const int nact = 64 - 4 * K;
-      const bool s_lo = (act0 >> lane) & 1ull, s_hi = (act0 >> (lane + 32)) & 1ull;
-      const double2 *fb = sh->f + luc_off(K) + __popcll(act0 & ((1ull << lane) - 1ull));
-      const double2 *fbh = sh->f + luc_off(K) + __popcll(act0 & ((1ull << (lane + 32)) - 1ull));
-      const int4 p4 = *reinterpret_cast<const int4 *>(sh->p[K]);
-      const int pp[4] = {p4.x, p4.y, p4.z, p4.w};
-      const int ncol = min(4, dr - 4 * K);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (c < ncol) {
-          const double2 flo = s_lo ? fb[c * nact] : make_double2(0.0, 0.0);
-          const double2 fhi = s_hi ? fbh[c * nact] : make_double2(0.0, 0.0);
-          done |= 1ull << pp[c];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) lu_rank1(lo[j], hi[j], pp[c], flo, fhi, true);
-        }
-      }
-    }
-    luc_panel(lo, hi, min(4, dr - 4 * J), done, sh, J, lane);
-    __syncwarp();
-    if (lane == 0) {
-      flow_publish(&sh->ready, base + J + 1);
-      flow_bar_arrive(&sh->bar[J]);
-    }
-  }
-  double2 det = make_double2(1.0, 0.0);
-  if (w == 0) {
-    flow_bar_wait(&sh->bar[nblocks - 1], parity);
-    int inv = 0;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int k = lane + 32 * half;
-      if (k < dr) {
-        const int pk = sh->p[k >> 2][k & 3];
-        det = cmul(det, sh->pv[k >> 2][k & 3]);
-        for (int k2 = 0; k2 < k; ++k2) inv += (sh->p[k2 >> 2][k2 & 3] > pk) ? 1 : 0;
       }
     }
 #pragma unroll

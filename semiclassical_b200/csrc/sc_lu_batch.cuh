@@ -36,7 +36,7 @@ k_lu_batch(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restri
 
 // left-looking dataflow variant (lu_det_left): 4 warps per matrix, 66 KB of shared memory, three matrices per SM
 template <int NW>
-__global__ void __launch_bounds__(32 * NW, (NW == 4 ? 3 : 3))
+__global__ void __launch_bounds__(32 * NW, 3)
 k_lu_left(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restrict__ det_out) {
   extern __shared__ __align__(16) unsigned char lu_smem[];
   LuFlow *sh = reinterpret_cast<LuFlow *>(lu_smem);
@@ -48,26 +48,6 @@ k_lu_left(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restric
   for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
     __syncthreads();   // barriers initialised / panels of the previous matrix no longer read
     const double2 det = lu_det_left<NW>(mats + (size_t)mat * dr * dr, dr, dr, sh, base, parity, w, lane);
-    base += nblocks;
-    parity ^= 1u;
-    if (t == 0) det_out[mat] = det;
-  }
-}
-
-// compact variant (luc_det_left): 35 KB of shared memory per matrix, up to six matrices per SM
-template <int NW, int OCC>
-__global__ void __launch_bounds__(32 * NW, OCC)
-k_lu_leftc(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restrict__ det_out) {
-  extern __shared__ __align__(16) unsigned char lu_smem[];
-  LuFlowC *sh = reinterpret_cast<LuFlowC *>(lu_smem);
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int nblocks = (dr + 3) >> 2;
-  luc_bar_init(sh, t);
-  int base = 0;
-  unsigned parity = 0;
-  for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
-    __syncthreads();
-    const double2 det = luc_det_left<NW>(mats + (size_t)mat * dr * dr, dr, dr, sh, base, parity, w, lane);
     base += nblocks;
     parity ^= 1u;
     if (t == 0) det_out[mat] = det;
@@ -88,28 +68,6 @@ static cudaError_t launch_lu_batch(const double2 *mats, int dr, int nmat, double
     int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 3);
     if (grid > nmat) grid = nmat;
     k_lu_mma<4, 3><<<grid, 128, smem, st>>>(mats, dr, nmat, det_out);
-    return cudaGetLastError();
-  }
-  if (dr > 32 && !getenv("SC_LU_NOCOMPACT")) {
-    int occ = 5;
-    if (const char *s2 = getenv("SC_LU_OCC")) occ = atoi(s2);
-    cudaError_t ce = cudaSuccess;
-    int grid = sm_count * (ctas_per_sm > 3 ? ctas_per_sm : occ);
-    if (grid > nmat) grid = nmat;
-#define SC_LUC(O)                                                                                                   \
-  ce = cudaFuncSetAttribute(k_lu_leftc<4, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LuFlowC));  \
-  if (ce != cudaSuccess) return ce;                                                                                 \
-  k_lu_leftc<4, O><<<grid, 128, sizeof(LuFlowC), st>>>(mats, dr, nmat, det_out);
-    if (occ >= 6) { SC_LUC(6) } else if (occ == 5) { SC_LUC(5) } else if (occ == 4) { SC_LUC(4) } else { SC_LUC(3) }
-#undef SC_LUC
-    return cudaGetLastError();
-  }
-  if (dr > 32 && getenv("SC_LU_NW8")) {
-    cudaError_t ce = cudaFuncSetAttribute(k_lu_left<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LuFlow));
-    if (ce != cudaSuccess) return ce;
-    int grid = sm_count * (ctas_per_sm > 0 ? ctas_per_sm : 3);
-    if (grid > nmat) grid = nmat;
-    k_lu_left<8><<<grid, 256, sizeof(LuFlow), st>>>(mats, dr, nmat, det_out);
     return cudaGetLastError();
   }
   if (dr > 32 && !getenv("SC_LU_BLK")) {

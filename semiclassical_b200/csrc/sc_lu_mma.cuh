@@ -25,14 +25,6 @@
 
 namespace sc {
 
-#ifdef LUM_PROF
-__device__ long long lum_prof[4][8];   // per warp: wait, update, transpose, panel columns, W, publish (bench only)
-#define LUM_T(i) { const long long t_ = clock64(); if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&lum_prof[w][i]), static_cast<unsigned long long>(t_ - tp_)); tp_ = t_; }
-#define LUM_T0() long long tp_ = clock64();
-#else
-#define LUM_T(i)
-#define LUM_T0()
-#endif
 
 struct LuMmaFixed {
   double2 pv[LU_MAX_PANELS][4];
@@ -273,17 +265,10 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
     // address arithmetic costs nothing there), else right before its own panel; they fly during the factorisation
     bool prefetched = false;
     const bool same = J + NW < nblocks;
-    LUM_T0()
 #pragma unroll 1
     for (int K = 0; K < J; ++K) {
       if (known <= K) {
         known = flow_peek(&sh->ready) - base;
-#if defined(LUM_SPIN)
-        while (known <= K) {
-          if (LUM_SPIN > 0) __nanosleep(LUM_SPIN);
-          known = flow_peek(&sh->ready) - base;
-        }
-#else
         if (known <= K) {
           if (!prefetched) {
             lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
@@ -292,9 +277,7 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
           flow_bar_wait(&sh->bar[K], parity);
           known = K + 1;
         }
-#endif
       }
-      LUM_T(0)
       const int pk = sh->p[K][j];
       const unsigned full = sh->tmask[K];
       const double2 *Wk = W + (size_t)K * LUM_PANEL_ELEMS + swl;
@@ -307,7 +290,6 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
       __syncwarp();                                              // ... and read before this update overwrites them
       const double b0 = part ? -x.y : -x.x, b1 = part ? -x.x : x.y;
       // the two k-steps of a tile are dependent (26 cycles); issue all first k-steps, then all second ones
-#ifndef LUM_SKIP_UPD
 #pragma unroll
       for (int T = 0; T < 8; ++T)
         if (!((full >> T) & 1u)) lum_dmma(acc[T][0], acc[T][1], wv[T].x, b0);
@@ -317,18 +299,11 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
           lum_dmma(acc[T][0], acc[T][1], wv[T].y, b1);
           WJ[T * 32 + swl] = make_double2(acc[T][0], acc[T][1]);
         }
-#endif
-      LUM_T(1)
     }
     if (J > 0) done = sh->dmask[J - 1];
     if (!prefetched) lum_load_block(same ? A : Anext, ld, dr, same ? J + NW : w, g, j, nxt);
     // the mirror is the transpose into the rows <-> lanes layout: factor, publish
     __syncwarp();
-#ifdef LUM_SKIP_PANEL
-    if (lane < 4) { sh->p[J][lane] = 4 * J + lane; sh->pv[J][lane] = make_double2(1.0, 0.0); }
-    if (lane == 0) { sh->dmask[J] = pad_rows | ((J + 1 < 16) ? ((1ull << (4 * J + 4)) - 1ull) : ~0ull); sh->tmask[J] = (1u << ((J + 1) >> 1)) - 1u; }
-    LUM_T(2)
-#else
     {
       const int sw = (lane >> 1) & 3, ncol = min(4, dr - 4 * J);
       const bool last = J + 1 == nblocks;
@@ -336,12 +311,10 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
       if (static_cast<unsigned>(done) == 0xffffffffu) {          // warp-uniform
 #pragma unroll
         for (int c = 0; c < 4; ++c) hi[c] = WJ[(lane + 32) * 4 + (c ^ sw)];
-        LUM_T(2)
         lum_panel1<true>(hi, ncol, done, ~pad_rows, last, sh, J, WJ, lane);
       } else if (static_cast<unsigned>(done >> 32) == 0xffffffffu) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) lo[c] = WJ[lane * 4 + (c ^ sw)];
-        LUM_T(2)
         lum_panel1<false>(lo, ncol, done, ~pad_rows, last, sh, J, WJ, lane);
       } else {
 #pragma unroll
@@ -349,18 +322,14 @@ __device__ __forceinline__ double2 lum_det(const double2 *__restrict__ A, const 
           lo[c] = WJ[lane * 4 + (c ^ sw)];
           hi[c] = WJ[(lane + 32) * 4 + (c ^ sw)];
         }
-        LUM_T(2)
         lum_panel(lo, hi, min(4, dr - 4 * J), done, ~pad_rows, last, sh, J, WJ, lane);
       }
     }
-#endif
-    LUM_T(3)
     __syncwarp();
     if (lane == 0) {
       flow_publish(&sh->ready, base + J + 1);
       flow_bar_arrive(&sh->bar[J]);
     }
-    LUM_T(4)
   }
   double2 det = make_double2(1.0, 0.0);
   if (w == 0) {

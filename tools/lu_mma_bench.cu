@@ -31,16 +31,6 @@ template <int OCC> static float run_mma(const double2 *dA, int dr, int nmat, dou
   k_lu_mma<4, OCC><<<grid, 128, smem>>>(dA, dr, nmat, ddet);
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
-#ifdef LUM_PROF
-  long long hp[4][8];
-  cudaMemcpyFromSymbol(hp, lum_prof, sizeof(hp));
-  const double nm = 2.0 * nmat;   // two launches, all CTAs accumulate
-  for (int w = 0; w < 4; ++w)
-    printf("      warp %d per matrix: wait %6.0f  update %6.0f  transpose %5.0f  panel %6.0f  publish %5.0f cycles\n", w,
-           hp[w][0] / nm, hp[w][1] / nm, hp[w][2] / nm, hp[w][3] / nm, hp[w][4] / nm);
-  long long z[4][8] = {};
-  cudaMemcpyToSymbol(lum_prof, z, sizeof(z));
-#endif
   return ms;
 }
 int main(int argc, char **argv) {
@@ -80,7 +70,7 @@ int main(int argc, char **argv) {
              ms * 1e-3 * 1.965e9 * 148 / nmat, maxerr, cudaGetErrorString(cudaGetLastError()));
     };
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    setenv("SC_LU_DFMA", "1", 1);
+    setenv("SC_LU_DFMA", "1", 1);   // the DFMA left-looking kernel k_lu_left<4> for comparison
     launch_lu_batch(dA, dr, nmat, ddet, 148, 0, 0);
     cudaDeviceSynchronize();
     cudaEventRecord(e0);
@@ -88,6 +78,7 @@ int main(int argc, char **argv) {
     cudaEventRecord(e1); cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     check("DFMA left-looking", ms);
+    unsetenv("SC_LU_DFMA");
     cudaMemset(ddet, 0, sizeof(double2) * nmat);
     ms = run_mma<3>(dA, dr, nmat, ddet, 3); check("DMMA occ3", ms);
     cudaMemset(ddet, 0, sizeof(double2) * nmat);

@@ -1,4 +1,5 @@
-"""per-kernel device times of the chunked pipeline under different CTA splits (are the two kernels co-resident?)"""
+"""per-kernel device times of the column pipeline (k_qp_path, k_rk4_wcols, k_lu_mma) from the engine's CUDA-event timing
+usage: pipeline_probe.py NTRAJ NSTEPS   (env: SC_CHUNK_K, SC_CHUNK_CTAS, SC_LU_CTAS, SC_WCOLS_TILES, SC_LU_DFMA)"""
 import os, sys, ctypes
 import numpy as np, torch
 sys.path.insert(0, '/root/repo')
@@ -23,4 +24,4 @@ e1.record(); torch.cuda.synchronize()
 kt = np.zeros(4)
 L.sc_engine_get_timing(pr._engine, kt.ctypes.data)
 wall = e0.elapsed_time(e1)
-print(f"CTAS={os.environ.get('SC_CHUNK_CTAS')} LU={os.environ.get('SC_LU_CTAS')} OVL={os.environ.get('SC_CHUNK_OVERLAP')}: wall {wall:.1f} ms, rk4 {kt[1]:.1f} ms, lu {kt[2]:.1f} ms, qp {kt[0]:.1f}  -> {n*K/wall*1e3:.4g} traj-steps/s")
+print(f"CTAS={os.environ.get('SC_CHUNK_CTAS')} LU={os.environ.get('SC_LU_CTAS')} K={os.environ.get('SC_CHUNK_K')}: wall {wall:.1f} ms, rk4 {kt[1]:.1f} ms, lu {kt[2]:.1f} ms, qp {kt[0]:.1f}  -> {n*K/wall*1e3:.4g} traj-steps/s")
