@@ -59,3 +59,26 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle/make_golden.py", ""), f"{f} mentions the oracle"
+
+
+def test_dynamics_driver_host_logic(tmp_path):
+    """`semi dynamics` driver (semiclassical_b200/dynamics.py): model-file parsing as cli.py:229-283, configuration
+    errors, and no CPU path"""
+    import numpy as np
+    import pytest
+    from semiclassical_b200 import dynamics, workloads
+    rows = workloads._AS5_ROWS
+    model_file = tmp_path / "AS_model.dat"
+    np.savetxt(model_file, np.column_stack((rows, np.full(len(rows), 0.02))), fmt="%.10f", header="omega S nac chi")
+    pot, q0, p0, G0, zpt = dynamics._as_model(str(model_file))
+    m = workloads.as_5modes(0.02)
+    assert np.allclose(q0.numpy(), m.q0, rtol=0, atol=1e-14) and float(abs(p0).max()) == 0.0
+    assert np.allclose(np.diag(G0.numpy()), m.omega, rtol=0, atol=1e-18) and abs(zpt - m.en_zpt) < 1e-16
+    assert pot.dimensions() == 5
+    task = {"potential": {"type": "no such potential"}, "results": {}}
+    with pytest.raises(dynamics.ConfigurationError):
+        dynamics.run_semiclassical_dynamics(task, device="cuda:0")
+    task = {"potential": {"type": "anharmonic AS", "model_file": str(model_file)}, "num_steps": 3, "time_step_fs": 0.01,
+            "num_trajectories": 10, "batch_size": 10, "results": {"correlations": str(tmp_path / "c.npz")}}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dynamics.run_semiclassical_dynamics(task, device="cpu")
