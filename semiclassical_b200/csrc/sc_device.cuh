@@ -166,8 +166,11 @@ __device__ __forceinline__ double pot_eval(const PotDev &P, const double *qs, do
       for (int i = t; i < d * d; i += TPT) H[(i / d) * ldh + (i % d)] = P.hess0[i];
     Group<TPT>::sync(gid);
     if (t < d) {
+      // H holds hess0 here (filled above, or still there from the first stage): read it from shared memory, not with
+      // d uncoalesced global loads per thread
       double hd = 0.0;
-      for (int j = 0; j < d; ++j) hd += P.hess0[t * d + j] * scr[j];
+      const double *hr = H + t * ldh;
+      for (int j = 0; j < d; ++j) hd += hr[j] * scr[j];
       g[t] = P.grad0[t] + hd;
       vpart = scr[t] * P.grad0[t] + 0.5 * scr[t] * hd;
     }
@@ -615,14 +618,16 @@ __device__ __forceinline__ void corr_terms(const EngDev &E, const double *q, con
       v[0] = -0.5 * (dq * E.otA[t] * dq + dp * E.otB[t] * dp);
       v[1] = -E.p0[t] * dq + dq * E.otC[t] * dp;
     } else {
+      // column t of A, B, C (coalesced across the threads): sum_t x_t (A^T x)_t = x A x, and
+      // sum_t dp_t (C^T dq)_t = dq C dp
       double sa = 0.0, sb = 0.0, sc_ = 0.0;
       for (int j = 0; j < d; ++j) {
-        sa += __ldg(E.otA + t * d + j) * dqv[j];
-        sb += __ldg(E.otB + t * d + j) * dpv[j];
-        sc_ += __ldg(E.otC + t * d + j) * dpv[j];
+        sa += __ldg(E.otA + j * d + t) * dqv[j];
+        sb += __ldg(E.otB + j * d + t) * dpv[j];
+        sc_ += __ldg(E.otC + j * d + t) * dqv[j];
       }
       v[0] = -0.5 * (dq * sa + dp * sb);
-      v[1] = -E.p0[t] * dq + dq * sc_;
+      v[1] = -E.p0[t] * dq + dp * sc_;
     }
     const double wr = E.wR[t], wg = E.wG[t];
     v[2] = dq * wr;

@@ -92,6 +92,120 @@ __device__ __forceinline__ double pot_local_vals(const PotDev &P, int t, double 
   return v;
 }
 
+// Dense-Gamma prefactor matrix on the tensor pipe (the DFMA version, prefactor_assemble in sc_device.cuh, took 80 % of
+// the step of a dense 60-mode model):
+//     Cm = 1/2 [ L1 Mqq R1 + L2 Mpp R2 - i L1 Mqp R2 + i L2 Mpq R1 ]            (propagators.py:969-994)
+// as four pairs of products  T = M_blk R_blk (d x dr, to shared memory),  C += +-L_blk T (dr x dr, accumulators
+// in registers across the four blocks).  8 x 8 output tiles are dealt round-robin to the NW warps; M_blk comes from the
+// monodromy slabs in shared memory; the constant factor matrices L_blk, R_blk are staged per block into S (the stage-
+// operand region, dead between stage 4 and the next step) with coalesced loads -- fetching their fragments straight
+// from L2 made the assembly latency bound (1.7 MB of fragment loads per trajectory-step instead of 0.2 MB).
+// T: >= ((d + 7) & ~7) rows x ldt; ldt and the staging leading dimensions are = 4 or 12 mod 16 (conflict-free fragments).
+__host__ __device__ constexpr int mma_frag_ld(int n) { return n % 16 == 4 || n % 16 == 12 ? n : (n % 4 == 0 ? ((n + 4) % 16 == 4 || (n + 4) % 16 == 12 ? n + 4 : n + 8) : mma_frag_ld((n + 3) & ~3)); }
+
+template <int NW>
+__device__ __forceinline__ void prefactor_assemble_mma(const EngDev &E, const double *Ub, const double *Vb, int ldu, double2 *Cm,
+                                                       int ldc, double *T, int ldt, double *S, int t, int warp, int lane) {
+  // work item = (row tile, group of 4 column tiles): one A fragment feeds 4 DMMAs.  At most 8 x 2 items per product.
+  constexpr int MAXI = (16 + NW - 1) / NW;
+  constexpr int TPT = 32 * NW;
+  const int d = E.d, dr = E.dr;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int mtA = (d + 7) >> 3, ntA = (dr + 7) >> 3, nk = (d + 3) >> 2, dk = 4 * nk;
+  const int ngr = (ntA + 3) >> 2, nitemsA = mtA * ngr, nitemsC = ntA * ngr;
+  const int ldr = mma_frag_ld(dr), ldl = mma_frag_ld(d);
+  double *Rs = S, *Ls = S + dk * ldr;                            // R_blk (dk x dr, zero rows beyond d), L_blk (dr x dk)
+  const bool kpad = (d & 3) != 0;                                // k-steps reach beyond d: the slab columns there are not zero
+  double cre[MAXI][4][2], cim[MAXI][4][2];
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i)
+#pragma unroll
+    for (int n = 0; n < 4; ++n) cre[i][n][0] = cre[i][n][1] = cim[i][n][0] = cim[i][n][1] = 0.0;
+#pragma unroll
+  for (int blk = 0; blk < 4; ++blk) {
+    // blk 0: Mqq (L1,R1) re ; 1: Mpp (L2,R2) re ; 2: Mqp (L1,R2) -im ; 3: Mpq (L2,R1) +im
+    const double *Mb = ((blk == 0 || blk == 2) ? Ub : Vb) + ((blk == 1 || blk == 2) ? d : 0);
+    const double *Lm = (blk == 0 || blk == 2) ? E.L1 : E.L2;
+    const double *Rm = (blk == 0 || blk == 3) ? E.R1 : E.R2;
+    const double sgn = (blk == 2) ? -1.0 : 1.0;
+    for (int idx = t; idx < dk * dr; idx += TPT) {
+      const int k = idx / dr, n = idx - k * dr;
+      Rs[k * ldr + n] = k < d ? __ldg(Rm + idx) : 0.0;
+    }
+    for (int idx = t; idx < dr * dk; idx += TPT) {
+      const int ap = idx / dk, a = idx - ap * dk;
+      Ls[ap * ldl + a] = a < d ? sgn * __ldg(Lm + ap * d + a) : 0.0;
+    }
+    __syncthreads();
+    // ---- T = M_blk R_blk.  Rows >= d of the last row tile repeat row d - 1 (finite; they meet zero columns of L),
+    // columns >= dr of the last column tile read the neighbouring row of Rs (finite; never stored)
+    for (int item = warp; item < nitemsA; item += NW) {
+      const int mt = item / ngr, n0 = 4 * (item - mt * ngr);
+      const int row = min(8 * mt + fr, d - 1);
+      const double *ap = Mb + row * ldu + fc;
+      const double *bp = Rs + fc * ldr + 8 * n0 + fr;
+      double c[4][2];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) c[n][0] = c[n][1] = 0.0;
+#pragma unroll 3
+      for (int kk = 0; kk < nk; ++kk) {
+        double a = ap[4 * kk];
+        if (kpad && 4 * kk + fc >= d) a = 0.0;
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+          if (n0 + n < ntA) dmma884(c[n][0], c[n][1], a, bp[4 * kk * ldr + 8 * n]);
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int col = 8 * (n0 + n) + 2 * fc;                        // columns >= dr would run into the next row
+        double *tp = T + (8 * mt + fr) * ldt + col;
+        if (col < dr) tp[0] = c[n][0];
+        if (col + 1 < dr) tp[1] = c[n][1];
+      }
+    }
+    __syncthreads();
+    // ---- C += +-L_blk T
+#pragma unroll
+    for (int i = 0; i < MAXI; ++i) {
+      const int item = warp + NW * i;
+      if (item < nitemsC) {                                      // warp-uniform
+        const int mt = item / ngr, n0 = 4 * (item - mt * ngr);
+        const int row = min(8 * mt + fr, dr - 1);
+        const double *ap = Ls + row * ldl + fc;
+        const double *bp = T + fc * ldt + 8 * n0 + fr;
+#pragma unroll 3
+        for (int kk = 0; kk < nk; ++kk) {
+          const double a = ap[4 * kk];
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+            if (n0 + n < ntA) {
+              if (blk < 2) dmma884(cre[i][n][0], cre[i][n][1], a, bp[4 * kk * ldt + 8 * n]);
+              else dmma884(cim[i][n][0], cim[i][n][1], a, bp[4 * kk * ldt + 8 * n]);
+            }
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < MAXI; ++i) {
+    const int item = warp + NW * i;
+    if (item < nitemsC) {
+      const int mt = item / ngr, n0 = 4 * (item - mt * ngr);
+      const int row = 8 * mt + fr;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int col = 8 * (n0 + n) + 2 * fc;
+        if (row < dr && n0 + n < ntA) {
+          if (col < dr) Cm[row * ldc + col] = make_double2(0.5 * cre[i][n][0], 0.5 * cim[i][n][0]);
+          if (col + 1 < dr) Cm[row * ldc + col + 1] = make_double2(0.5 * cre[i][n][1], 0.5 * cim[i][n][1]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int WM, int WN, int NWM, int NWN, int MC>
 __global__ void __launch_bounds__(32 * NWM * NWN, 1)
 k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, double *partials, SmemLayout L, int traj0,
@@ -352,7 +466,12 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
         }
       } else {
         const int ldc = dr | 1;
-        prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, ldc, H, t, gid);
+        // staging of the factor matrices needs d ldr + dr ldl doubles of the stage-operand region (it does for every
+        // supported d; the DFMA version is the fallback)
+        if (DK * mma_frag_ld(dr) + dr * mma_frag_ld(d) <= DK * ldu)
+          prefactor_assemble_mma<NW>(E, Ub, Vb, ldu, Cm, ldc, H, ldh, Us, t, warp, lane);
+        else
+          prefactor_assemble<TPT>(E, Ub, Vb, ldu, Cm, ldc, H, t, gid);
 #pragma unroll
         for (int m = 0; m < MC; ++m) {
           const int a = warp + NW * m;
