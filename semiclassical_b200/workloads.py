@@ -92,3 +92,22 @@ def gdml_synthetic(n_atoms=17, n_train=200, sig=80, seed=99, alpha_rms=2.0e3):
         'perms': np.arange(n_atoms)[None, :], 'tril_perms_lin': np.arange(D),
     }
     return model, pos.reshape(-1)
+
+
+def harmonic_molecule_synthetic(dim=60, nzero=6, seed=3):
+    """
+    synthetic harmonic 'molecule' with the shape of the reference's molecular use case (C3 at size dim): dense
+    Hessian with `nzero` zero modes (translations / rotations), unit masses, width matrix Gamma_0 = sqrt(Hessian)
+    (rank dim - nzero, dense), wavepacket displaced along the vibrations only.
+    Returns dict(pos0, hess0, grad0, energy0, masses, nac, Gamma_0, q0, p0, en_zpt).
+    """
+    rng = np.random.default_rng(seed)
+    V, _ = np.linalg.qr(rng.standard_normal((dim, dim)))
+    w = np.concatenate((np.zeros(nzero), np.linspace(200.0, 3400.0, dim - nzero) / units.hartree_to_wavenumbers))
+    G0 = (V * w[None, :]) @ V.T
+    hess = (V * (w * w)[None, :]) @ V.T
+    pos0 = rng.standard_normal(dim)
+    q0 = pos0 + V[:, nzero:] @ (0.3 * rng.standard_normal(dim - nzero) / np.sqrt(w[nzero:]))
+    return dict(pos0=pos0, hess0=0.5 * (hess + hess.T), grad0=np.zeros(dim), energy0=0.0, masses=np.ones(dim),
+                nac=1.0e-3 * rng.standard_normal(dim), Gamma_0=0.5 * (G0 + G0.T), q0=q0, p0=np.zeros(dim),
+                en_zpt=float(0.5 * w.sum()))

@@ -359,3 +359,32 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
     data3 = dict(np.load(out))
     assert abs(data3['autocorrelation'][0] - 1.0) < 1.0e-9
     assert relerr(data3['autocorrelation'], g['autocorrelation']) < 0.2
+
+
+# ------------------------------------------------------------------ general path: dense Gamma, rank deficient
+@pytest.mark.parametrize("d", [23, 40, 54])
+def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
+    """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on k_hk_mma in split mode: DMMA prefactor
+    assembly (k-padding at d = 23), batched LU with d' = 17 (k_lu_batch), 34 (k_lu_mma, ragged last panel), 48"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.harmonic_molecule_synthetic(d)
+    G = m['Gamma_0']
+    n, nt = 157, 9
+    zi, probi = oracle.sample_ensemble(G, G, m['q0'], m['p0'], n, np.random.default_rng(200 + d))
+    dt, _ = workloads.test_time_grid()
+    opot = oracle.Potential.harmonic(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    ref = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt, m['en_zpt'])
+    pot = potentials.MolecularHarmonicPotential.from_arrays(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m['q0']), T(m['p0']), T(G), T(zi), T(probi))
+    a0, i0 = pr.autocorrelation(m['en_zpt']), pr.ic_correlation(pot, m['en_zpt'])
+    a, i = pr.propagate(pot, dt, nt - 1, m['en_zpt'])
+    assert pr.kernel_name().startswith("k_hk_mma+")
+    assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    ref2 = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt, m['en_zpt'])
+    assert relerr(pr.y.cpu().numpy(), ref2['y']) < TOL
+    assert relerr(pr.c.cpu().numpy(), ref2['c']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
