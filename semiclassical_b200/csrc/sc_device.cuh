@@ -127,7 +127,8 @@ __device__ __forceinline__ void group_reduce(double (&v)[N], double *red, int t,
 // `scr` is a d-vector of shared scratch.  Ends with the results visible to the whole group.
 template <int TPT>
 __device__ __forceinline__ double pot_eval(const PotDev &P, const double *qs, double *g, double *H, int ldh,
-                                           double *scr, double *scr2, int t, int gid, bool fill_h) {
+                                           double *scr, double *scr2, int t, int gid, bool fill_h,
+                                           bool rotated_h_by_caller = false) {
   const int d = P.d;
   double vpart = 0.0;
   if (P.type == POT_MORSE || P.type == POT_NONHARMONIC) {
@@ -203,12 +204,14 @@ __device__ __forceinline__ double pot_eval(const PotDev &P, const double *qs, do
       for (int k = 0; k < d; ++k) s += P.Q[t * d + k] * scr[k];
       g[t] = s;
     }
-    for (int idx = t; idx < d * d; idx += TPT) {
-      const int i = idx / d, j = idx % d;
-      double s = 0.0;
-      for (int k = 0; k < d; ++k) s += P.Q[i * d + k] * scr2[k] * P.Q[j * d + k];
-      H[i * ldh + j] = s;
-    }
+    // H = Q diag(h) Q^T; the tensor-core kernel forms it itself from scr2 (rotated_hessian_mma, sc_mma.cuh)
+    if (!rotated_h_by_caller)
+      for (int idx = t; idx < d * d; idx += TPT) {
+        const int i = idx / d, j = idx % d;
+        double s = 0.0;
+        for (int k = 0; k < d; ++k) s += P.Q[i * d + k] * scr2[k] * P.Q[j * d + k];
+        H[i * ldh + j] = s;
+      }
   }
   Group<TPT>::sync(gid);
   return vpart;

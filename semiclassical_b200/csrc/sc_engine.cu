@@ -555,7 +555,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   }
   const int dp = (d + 1) & ~1;
   const size_t per_traj = (size_t)KC * ((size_t)d * d * sizeof(double2) + sizeof(double2) + 8 * sizeof(double) + 4 * dp * sizeof(double));
-  size_t budget = (size_t)3 << 30;
+  size_t budget = (size_t)6 << 30   /* windows of >= 5 000 trajectories at 20 steps per pass (60 modes) */;
   if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
   long long ntb = (long long)(budget / per_traj);
   ntb = (ntb / sm) * sm;

@@ -92,6 +92,44 @@ __device__ __forceinline__ double pot_local_vals(const PotDev &P, int t, double 
   return v;
 }
 
+// H = Q diag(h) Q^T of the rotated-AS potential (potentials of the dense parity fixtures) on the tensor pipe:
+// work item = (row tile, group of 4 column tiles); A fragment = Q[i][k] h[k], B fragment = Q[j][k], both straight from
+// the L1/L2-resident Q (28.8 KB at d = 60).  The scalar version (pot_eval) needed d^3 global loads per stage.
+// hk: shared vector of the d inner second derivatives.  Ends with a CTA barrier.
+template <int NW>
+__device__ __forceinline__ void rotated_hessian_mma(const PotDev &P, const double *hk, double *H, int ldh, int warp, int lane) {
+  const int d = P.d;
+  const int fr = lane >> 2, fc = lane & 3;
+  const int mt_n = (d + 7) >> 3, nk = (d + 3) >> 2, ngr = (mt_n + 3) >> 2;
+  for (int item = warp; item < mt_n * ngr; item += NW) {
+    const int mt = item / ngr, n0 = 4 * (item - mt * ngr);
+    const double *ap = P.Q + (size_t)min(8 * mt + fr, d - 1) * d + fc;
+    double c[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) c[n][0] = c[n][1] = 0.0;
+#pragma unroll 3
+    for (int kk = 0; kk < nk; ++kk) {
+      const bool kok = 4 * kk + fc < d;
+      const double a = kok ? __ldg(ap + 4 * kk) * hk[4 * kk + fc] : 0.0;
+#pragma unroll
+      for (int n = 0; n < 4; ++n)
+        if (n0 + n < mt_n) {
+          const double b = kok ? __ldg(P.Q + (size_t)min(8 * (n0 + n) + fr, d - 1) * d + 4 * kk + fc) : 0.0;
+          dmma884(c[n][0], c[n][1], a, b);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int row = 8 * mt + fr, col = 8 * (n0 + n) + 2 * fc;
+      if (row < d && n0 + n < mt_n) {
+        if (col < d) H[row * ldh + col] = c[n][0];
+        if (col + 1 < d) H[row * ldh + col + 1] = c[n][1];
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // Dense-Gamma prefactor matrix on the tensor pipe (the DFMA version, prefactor_assemble in sc_device.cuh, took 80 % of
 // the step of a dense 60-mode model):
 //     Cm = 1/2 [ L1 Mqq R1 + L2 Mpp R2 - i L1 Mqp R2 + i L2 Mpq R1 ]            (propagators.py:969-994)
@@ -137,8 +175,8 @@ __device__ __forceinline__ void prefactor_assemble_mma(const EngDev &E, const do
       Ls[ap * ldl + a] = a < d ? sgn * __ldg(Lm + ap * d + a) : 0.0;
     }
     __syncthreads();
-    // ---- T = M_blk R_blk.  Rows >= d of the last row tile repeat row d - 1 (finite; they meet zero columns of L),
-    // columns >= dr of the last column tile read the neighbouring row of Rs (finite; never stored)
+    // ---- T = M_blk R_blk.  Rows >= d of the last row tile repeat row d - 1 and columns >= dr of the last column tile
+    // read the neighbouring row of Rs (finite; neither is stored)
     for (int item = warp; item < nitemsA; item += NW) {
       const int mt = item / ngr, n0 = 4 * (item - mt * ngr);
       const int row = min(8 * mt + fr, d - 1);
@@ -159,8 +197,10 @@ __device__ __forceinline__ void prefactor_assemble_mma(const EngDev &E, const do
       for (int n = 0; n < 4; ++n) {
         const int col = 8 * (n0 + n) + 2 * fc;                        // columns >= dr would run into the next row
         double *tp = T + (8 * mt + fr) * ldt + col;
-        if (col < dr) tp[0] = c[n][0];
-        if (col + 1 < dr) tp[1] = c[n][1];
+        if (8 * mt + fr < d) {                                        // the padding rows of T (= of H) stay zero
+          if (col < dr) tp[0] = c[n][0];
+          if (col + 1 < dr) tp[1] = c[n][1];
+        }
       }
     }
     __syncthreads();
@@ -301,7 +341,8 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
         // the dense prefactor assembly uses H as scratch: refill every step
         for (int i = t; i < ((d + 7) & ~7) * ldh; i += TPT) H[i] = 0.0;
         __syncthreads();
-        vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, true);
+        vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, true, true);
+        if (P.type == POT_ROTATED_MORSE) rotated_hessian_mma<NW>(P, scr2, H, ldh, warp, lane);
       }
       PT(1);
 #pragma unroll 1
@@ -418,7 +459,10 @@ k_hk_mma(EngDev E, PotDev P, double h, int nsteps, int step0, int nsteps_total, 
         }
         __syncthreads();
         PT(3);
-        if (s < 4 && !separable) vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, P.type == POT_ROTATED_MORSE);
+        if (s < 4 && !separable) {
+          vpart = pot_eval<TPT>(P, qs, g, H, ldh, scr, scr2, t, gid, P.type == POT_ROTATED_MORSE, true);
+          if (P.type == POT_ROTATED_MORSE) rotated_hessian_mma<NW>(P, scr2, H, ldh, warp, lane);
+        }
         PT(1);
       }
       if (separable && t < d) { accS = sacc[t]; e4 = se4[t]; }
