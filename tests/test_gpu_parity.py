@@ -388,3 +388,51 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     assert relerr(pr.y.cpu().numpy(), ref2['y']) < TOL
     assert relerr(pr.c.cpu().numpy(), ref2['c']) < TOL
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
+
+
+# ------------------------------------------------------------------ BASELINE size: size-independent properties
+def test_full_size_properties_c4(cuda_device):
+    """configs[3] at its full single-GPU size (10^6 trajectories, 60 modes, ~116 GB of state) where no oracle run is
+    affordable: C(0) = 1 exactly (Gamma_i = Gamma_0, cli.py:460-467), the correlation functions are linear in the
+    ensemble (two half ensembles normalised by the global N add up to the whole), a repeated run is bitwise identical,
+    and a 1 000-trajectory subset agrees with the C oracle"""
+    import gc
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    free, _ = torch.cuda.mem_get_info(torch.device(cuda_device))
+    n = 1000000 if free > 150e9 else 200000
+    m = workloads.as_synthetic(60)
+    G = np.diag(m.omega)
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(2024))
+    dt, _ = workloads.test_time_grid()
+    nt = 20
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+
+    def run(sl, repeat=False):
+        pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+        pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi[:, sl]), T(probi[sl]), ntraj_total=n)
+        c0 = pr.autocorrelation(m.en_zpt)
+        a, i = pr.propagate(pot, dt, nt, m.en_zpt)
+        if repeat:
+            pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi[:, sl]), T(probi[sl]), ntraj_total=n)
+            a2, i2 = pr.propagate(pot, dt, nt, m.en_zpt)
+            assert np.array_equal(a, a2) and np.array_equal(i, i2)
+        del pr
+        gc.collect()
+        torch.cuda.empty_cache()
+        return c0, a, i
+
+    c0, a, i = run(slice(0, n), repeat=True)
+    assert abs(c0 - 1.0) < 1.0e-9
+    assert np.all(np.isfinite(a)) and np.all(np.isfinite(i))
+    h = n // 2 + 12345
+    c0a, aa, ia = run(slice(0, h))
+    c0b, ab, ib = run(slice(h, n))
+    assert abs(c0a + c0b - c0) < 1.0e-12
+    assert relerr(aa + ab, a) < 1.0e-12 and relerr(ia + ib, i) < 1.0e-12
+    # subset vs oracle (normalised by the same global N)
+    ns = 1000
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi[:, :ns].copy(),
+                     probi[:ns].copy(), dt, nt + 1, m.en_zpt, ntraj_norm=n)
+    _, asub, isub = run(slice(0, ns))
+    assert relerr(asub, ref['autocorrelation'][1:]) < TOL and relerr(isub, ref['ic_correlation'][1:]) < TOL
