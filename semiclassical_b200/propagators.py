@@ -98,6 +98,25 @@ class CoherentStatesOverlap(object):
         return self.fac.to(dev) * torch.exp(expo)
 
 
+class CoherentStatesWavefunction(object):
+    """phi(x) = sum_i v_i <x|q_i,p_i,G> on a spatial grid (propagators.py:241-290); plain torch on the tensors' device --
+    the propagators evaluate the same sum with the tensor-core kernel behind `wavefunction(x)`"""
+    def __init__(self, G):
+        self.G = G
+        _, self.detG, self.rank = _pinv_sym(G.detach().to('cpu', torch.float64))
+
+    def __call__(self, q, p, v, x):
+        d, nx = x.size()
+        dim, ntraj = q.size()
+        assert d == dim, "dimensions of spatial grid and coherent states differ"
+        G = self.G.to(device=x.device, dtype=torch.float64)
+        dx = x.unsqueeze(1) - q.unsqueeze(2)                      # (dim, ntraj, nx)
+        fac = (self.detG / np.pi**self.rank)**0.25
+        gaussians = fac * torch.exp(-0.5 * torch.einsum('inx,ij,jnx->nx', dx, G, dx)
+                                    + 1j / hbar * torch.einsum('in,inx->nx', p, dx))
+        return torch.sum(v.unsqueeze(1) * gaussians, 0)
+
+
 def _np(x):
     return np.ascontiguousarray(x.detach().to('cpu', torch.float64).numpy())
 

@@ -82,3 +82,29 @@ def test_dynamics_driver_host_logic(tmp_path):
             "num_trajectories": 10, "batch_size": 10, "results": {"correlations": str(tmp_path / "c.npz")}}
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dynamics.run_semiclassical_dynamics(task, device="cpu")
+
+
+def test_coherent_state_helpers_match_oracle():
+    """the plain-torch mirrors of CoherentStatesOverlap / CoherentStatesWavefunction (propagators.py:124-290) against
+    the numpy restatement, including a rank-deficient width matrix (zero-mode invariance, test_propagators.py:73-113)"""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    from semiclassical_b200 import propagators
+    torch.set_default_dtype(torch.float64)
+    rng = np.random.default_rng(11)
+    d, ni, nj = 4, 5, 3
+    V, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    for w in (np.array([0.5, 1.0, 2.0, 3.0]), np.array([0.0, 1.0, 2.0, 3.0])):
+        G = (V * w[None, :]) @ V.T
+        G = 0.5 * (G + G.T)
+        qi, pi, qj, pj = (rng.standard_normal((d, n)) for n in (ni, ni, nj, nj))
+        cs = propagators.CoherentStatesOverlap(torch.from_numpy(G), torch.from_numpy(G))
+        O = cs(*(torch.from_numpy(x) for x in (qi, pi, qj, pj))).numpy()
+        assert np.abs(O - oracle.overlap(G, G, qi, pi, qj, pj)).max() < 1e-13
+        v = rng.standard_normal(ni) + 1j * rng.standard_normal(ni)
+        x = rng.standard_normal((d, 7))
+        csw = propagators.CoherentStatesWavefunction(torch.from_numpy(G))
+        phi = csw(torch.from_numpy(qi), torch.from_numpy(pi), torch.from_numpy(v), torch.from_numpy(x)).numpy()
+        y = np.concatenate((qi, pi, np.zeros((1, ni))), axis=0)
+        assert np.abs(phi - oracle.hk_wavefunction(G, y, v, x)).max() < 1e-13
