@@ -193,7 +193,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int NK, int NTW>
 __global__ void __launch_bounds__(128, (NTW == 1 ? 3 : 2))
 k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double2 *__restrict__ cm,
-            const double *__restrict__ hd, WColsLayout L) {
+            const double *__restrict__ hd, WColsLayout L, unsigned long long *__restrict__ queue) {
   constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
   constexpr int LDH = cols_ldh(NK), DK = 4 * NK;
   extern __shared__ __align__(16) double smem[];
@@ -233,7 +233,13 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
   const long long nitems = (long long)ntb * nitem;
   const int nhd = 4 * dp;
   const int c16_123 = 3 * dp / 2, c16_4 = dp / 2;       // 16-byte pieces of the stage 1-3 rows / of the stage-4 row
-  for (long long item = (long long)blockIdx.x * 4 + warp; item < nitems; item += (long long)gridDim.x * 4) {
+  // items are handed out dynamically (one atomic per ~100 us item): no tail of warps with one item more than others
+  auto next_item = [&]() {
+    unsigned long long v = 0ull;
+    if (lane == 0) v = atomicAdd(queue, 1ull);
+    return static_cast<long long>(__shfl_sync(0xffffffffu, v, 0));
+  };
+  for (long long item = next_item(); item < nitems; item = next_item()) {
     const int tl = static_cast<int>(item / nitem), it = static_cast<int>(item - (long long)tl * nitem);
     const int traj = traj0 + tl;
     int b[NTW];
@@ -391,24 +397,26 @@ k_rk4_wcols(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double
 
 template <int NK, int NTW>
 static cudaError_t launch_wcols_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb,
-                                  double2 *cm, const double *hd, const WColsLayout &L, cudaStream_t st) {
+                                  double2 *cm, const double *hd, const WColsLayout &L, unsigned long long *queue, cudaStream_t st) {
   cudaError_t ce = cudaFuncSetAttribute(k_rk4_wcols<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
   // full shared-memory carve-out: CTAs of the LU kernel can become resident next to this kernel's without an SM re-configuration
   ce = cudaFuncSetAttribute(k_rk4_wcols<NK, NTW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (ce != cudaSuccess) return ce;
-  k_rk4_wcols<NK, NTW><<<grid, 128, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L);
+  ce = cudaMemsetAsync(queue, 0, sizeof(unsigned long long), st);   // work queue of this launch
+  if (ce != cudaSuccess) return ce;
+  k_rk4_wcols<NK, NTW><<<grid, 128, smem, st>>>(E, P, h, nsteps, traj0, ntb, cm, hd, L, queue);
   return cudaGetLastError();
 }
 
 static cudaError_t launch_wcols(int grid, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb, double2 *cm,
-                                const double *hd, const WColsLayout &L, cudaStream_t st) {
+                                const double *hd, const WColsLayout &L, unsigned long long *queue, cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)L.total;
   switch (L.dk / 4) {
 #define SC_WCOLS_CASE(N)                                                                                              \
   case N:                                                                                                             \
-    return L.ntw == 2 ? launch_wcols_t<N, 2>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st)                 \
-                      : launch_wcols_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, st);
+    return L.ntw == 2 ? launch_wcols_t<N, 2>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, queue, st)          \
+                      : launch_wcols_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, queue, st);
     SC_WCOLS_CASE(9) SC_WCOLS_CASE(10) SC_WCOLS_CASE(11) SC_WCOLS_CASE(12) SC_WCOLS_CASE(13) SC_WCOLS_CASE(14) SC_WCOLS_CASE(15)
     SC_WCOLS_CASE(16)
 #undef SC_WCOLS_CASE

@@ -576,6 +576,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   double2 *det = cm + (size_t)KC * ntb * d * d;
   double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
   double *hd = aux + (size_t)KC * ntb * 8;
+  unsigned long long *queue = reinterpret_cast<unsigned long long *>(hd + (size_t)KC * ntb * 4 * dp);   // work queue of k_rk4_wcols
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
@@ -602,7 +603,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
       mark();
-      CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, st));
+      CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, queue, st));
       mark();
       CU(launch_lu_batch(cm, d, ks * nt, det, sm, (int)lu_per_sm, st));
       mark();
