@@ -31,9 +31,9 @@ sys.path.insert(0, ROOT)
 from semiclassical_b200 import workloads  # noqa: E402
 
 # DRAM traffic of the dominant kernel per trajectory-step, from the committed `ncu --set full` captures
-# (profiles/ncu_r01_c_k_rk4_cols.txt: dram__bytes_read.sum + dram__bytes_write.sum over 35 520 trajectory-steps;
-#  profiles/ncu_r01_f_k_rk4_wcols.txt: one launch of 4 884 trajectories x 10 steps)
-TRAFFIC_BYTES_PER_TRAJ_STEP = {"k_rk4_cols": (592.7e6 + 2554.9e6) / 35520.0, "k_rk4_wcols": (742.0e6 + 3728.3e6) / 48840.0}
+# (dram__bytes_read.sum + dram__bytes_write.sum;
+#  profiles/ncu_r01_f_k_rk4_wcols.txt: one launch of 9 768 trajectories x 10 steps)
+TRAFFIC_BYTES_PER_TRAJ_STEP = {"k_rk4_wcols": (1528.7e6 + 7494.6e6) / 97680.0}
 FLOP_PER_TRAJ_STEP = lambda d, dr, dense: 16.0 * d**3 + (8.0 / 3.0) * dr**3 + (8.0 * dr * d * d + 8.0 * dr * dr * d if dense else 0.0)  # noqa: E731
 
 
