@@ -20,7 +20,7 @@ import os
 import numpy as np
 import torch
 
-from semiclassical_b200 import potentials, propagators, units
+from semiclassical_b200 import distributed, potentials, propagators, units
 from semiclassical_b200.units import hbar
 
 logger = logging.getLogger(__name__)
@@ -133,7 +133,7 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
             propagator = propagators.WaltonManolopoulosPropagator(Gamma_i, Gamma_t, alpha, alpha, device=device)
         else:
             propagator = propagators.HermanKlukPropagator(Gamma_i, Gamma_t, device=device)
-        lo, hi = rank * num_samples // world, (rank + 1) * num_samples // world
+        lo, hi = distributed.shard_bounds(num_samples, rank, world)
         if ensembles is not None:
             zi, probi = ensembles[repetition]
             propagator.set_ensemble(q0, p0, Gamma_0, torch.as_tensor(zi)[:, lo:hi], torch.as_tensor(probi)[lo:hi],
