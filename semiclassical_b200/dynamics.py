@@ -126,13 +126,15 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
     group = True if world > 1 else None
 
     data = None
+    # one propagator for all repetitions (the reference builds a new one each time, cli.py:376-383): a new ensemble of the
+    # same size reuses the engine and its device buffers, and installing it resets time, state and branch trackers
+    if propagator_name == "WM":
+        alpha = task.get('cell_width', 10000.0)
+        propagator = propagators.WaltonManolopoulosPropagator(Gamma_i, Gamma_t, alpha, alpha, device=device)
+    else:
+        propagator = propagators.HermanKlukPropagator(Gamma_i, Gamma_t, device=device)
     for repetition in range(num_repetitions):
         logger.info(f"*** Repetition {repetition+1} ***")
-        if propagator_name == "WM":
-            alpha = task.get('cell_width', 10000.0)
-            propagator = propagators.WaltonManolopoulosPropagator(Gamma_i, Gamma_t, alpha, alpha, device=device)
-        else:
-            propagator = propagators.HermanKlukPropagator(Gamma_i, Gamma_t, device=device)
         lo, hi = distributed.shard_bounds(num_samples, rank, world)
         if ensembles is not None:
             zi, probi = ensembles[repetition]

@@ -351,6 +351,14 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
     data2 = dict(np.load(out))
     assert int(data2['trajectories']) == 2 * n
     assert relerr(data2['autocorrelation'], data['autocorrelation']) < 1.0e-13
+    # two repetitions in one call (one propagator, buffers reused): running average of identical ensembles
+    task["results"]["overwrite"] = True
+    task["num_trajectories"] = 2 * n
+    dynamics.run_semiclassical_dynamics(task, device=cuda_device, ensembles=[(g['zi'], g['probi'])] * 2, steps_per_launch=33)
+    data4 = dict(np.load(out))
+    assert int(data4['trajectories']) == 2 * n
+    assert relerr(data4['autocorrelation'], g['autocorrelation']) < TOL and relerr(data4['ic_correlation'], g['ic_correlation']) < TOL
+    task["num_trajectories"] = n
     # sampled on the device (torch CUDA generator): C(0) = 1 and the statistical agreement the reference tests ask for
     task["results"]["overwrite"] = True
     task["manual_seed"] = 0
