@@ -32,6 +32,7 @@ extern "C" {
 
 #define SC_ABI_VERSION 1
 #define SC_MAX_DIM 64         /* largest number of degrees of freedom the fused kernels accept */
+#define SC_TIMING_SLOTS 8     /* per-kernel timing slots: path, rk4, lu, finish, rmult, potential Hessians */
 
 typedef struct sc_potential sc_potential; /* opaque: device-resident potential parameters */
 typedef struct sc_engine sc_engine;       /* opaque: one propagator instance (ensemble + constants) on one GPU */
@@ -167,6 +168,9 @@ long long sc_engine_launch_count(const sc_engine *eng);
  * branch tracking + contributions } -- bench.py's roofline figure of the dominant kernel */
 int sc_engine_set_timing(sc_engine *eng, int on);
 int sc_engine_get_timing(sc_engine *eng, double *ms4_host);
+/* all SC_TIMING_SLOTS slots: { path (+ overlap terms), RK4/monodromy, LU, finish, right factors (k_rmult), potential
+ * Hessians, 0, 0 } of the column pipelines (propagators.py:645-655 has no counterpart: instrumentation only) */
+int sc_engine_get_timing_slots(sc_engine *eng, double *ms_host, int nslots);
 /* name of the fused kernel variant the last sc_engine_step dispatched to (diagnostics) */
 const char *sc_engine_kernel_name(const sc_engine *eng);
 

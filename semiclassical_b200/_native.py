@@ -96,6 +96,7 @@ _SIGNATURES = {
     "sc_engine_kernel_name": (ctypes.c_char_p, [_vp]),
     "sc_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "sc_engine_get_timing": (ctypes.c_int, [_vp, _vp]),
+    "sc_engine_get_timing_slots": (ctypes.c_int, [_vp, _vp, ctypes.c_int]),
 }
 
 

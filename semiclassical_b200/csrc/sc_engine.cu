@@ -15,6 +15,7 @@
 #include "sc_kernels.cuh"
 #include "sc_mma.cuh"
 #include "sc_chunk.cuh"
+#include "sc_stream.cuh"
 #include "sc_lu_batch.cuh"
 #include "sc_potentials.cuh"
 #include "sc_wm.cuh"
@@ -106,7 +107,11 @@ struct sc_engine {
   bool timing = false;
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
-  double tms[4] = {0.0, 0.0, 0.0, 0.0};   // k_qp_path, k_rk4_*, k_lu_*, k_hk_finish
+  std::vector<int> tev_slot;              // slot of the kernel(s) that follow the event, -1: end of a window
+  double tms[SC_TIMING_SLOTS] = {0.0};    // path (+aux), rk4, lu, finish, rmult, potential Hessians
+  // dense column pipeline (sc_stream.cuh): padded constant A operands
+  double *stream_const = nullptr;         // [H0 | L1 | L2], each d x ldh
+  const void *stream_h0_src = nullptr;    // potential whose Hessian sits in stream_const
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
   long long ntraj_norm = 0;
@@ -121,6 +126,7 @@ struct sc_engine {
     if (partials) cudaFree(partials);
     if (corr_dev) cudaFree(corr_dev);
     if (chunk_scratch) cudaFree(chunk_scratch);
+    if (stream_const) cudaFree(stream_const);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
 };
@@ -473,6 +479,20 @@ static int set_nac(sc_engine *e, const double *n1, cudaStream_t st) {
   return SC_OK;
 }
 
+// per-kernel timing (sc_engine_set_timing): an event before every kernel group, tagged with the slot its time goes to
+enum { TS_PATH = 0, TS_RK4 = 1, TS_LU = 2, TS_FINISH = 3, TS_RMULT = 4, TS_POT = 5, TS_END = -1 };
+static void timing_mark(sc_engine *e, int slot, cudaStream_t st) {
+  if (!e->timing) return;
+  if (e->tev_used == e->tev.size()) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->tev.push_back(ev);
+    e->tev_slot.push_back(TS_END);
+  }
+  e->tev_slot[e->tev_used] = slot;
+  cudaEventRecord(e->tev[e->tev_used++], st);
+}
+
 struct LaunchPlan {
   int tpt, ept, groups_per_cta, threads, grid;
   size_t smem;
@@ -583,15 +603,6 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   long long rk4_per_sm = LW.ntw == 2 ? 2 : 3, lu_per_sm = 0;   // 0: the LU launcher's default occupancy
   if (const char *s = getenv("SC_CHUNK_CTAS")) rk4_per_sm = atoi(s) > 0 ? atoi(s) : rk4_per_sm;
   if (const char *s = getenv("SC_LU_CTAS")) lu_per_sm = atoi(s) > 0 ? atoi(s) : lu_per_sm;
-  auto mark = [&]() {                       // per-kernel timing (sc_engine_set_timing): 5 events per window
-    if (!e->timing) return;
-    if (e->tev_used == e->tev.size()) {
-      cudaEvent_t ev;
-      cudaEventCreate(&ev);
-      e->tev.push_back(ev);
-    }
-    cudaEventRecord(e->tev[e->tev_used++], st);
-  };
   for (int s0 = 0; s0 < nsteps; s0 += KC) {
     const int ks = std::min(KC, nsteps - s0);
     size_t g0 = 0;
@@ -599,18 +610,18 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
       const int nt = (int)std::min<long long>(ntb, n - t0);
       long long grid = ((long long)nt * LW.nitem + 3) / 4;
       if (grid > rk4_per_sm * sm) grid = rk4_per_sm * sm;
-      mark();
+      timing_mark(e, TS_PATH, st);
       k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);
       CU(cudaGetLastError());
-      mark();
+      timing_mark(e, TS_RK4, st);
       CU(launch_wcols((int)grid, e->dev, P, h, ks, (int)t0, nt, cm, hd, LW, queue, st));
-      mark();
+      timing_mark(e, TS_LU, st);
       CU(launch_lu_batch(cm, d, ks * nt, det, sm, (int)lu_per_sm, st));
-      mark();
+      timing_mark(e, TS_FINISH, st);
       const int nblk = (nt + 127) / 128;
       k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
       CU(cudaGetLastError());
-      mark();
+      timing_mark(e, TS_END, st);
       g0 += nblk;
       e->launches += 4;
     }
@@ -619,6 +630,122 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   CU(cudaGetLastError());
   e->launches += 1;
   e->kernel_name = "k_rk4_wcols+k_lu_mma+k_hk_finish";
+  return SC_OK;
+}
+
+// dense column pipeline (sc_stream.cuh): path kernel -> overlap terms -> k_rk4_stream -> (dense widths: k_rmult) -> batched
+// LU -> branch tracking + contributions, window by window, KC time steps per pass
+__global__ void k_pad_matrix(const double *__restrict__ src, int rows, int cols, double *__restrict__ dst, int drows, int ld) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < drows * ld; i += gridDim.x * blockDim.x) {
+    const int r = i / ld, c = i - r * ld;
+    dst[i] = (r < rows && c < cols) ? src[(size_t)r * cols + c] : 0.0;
+  }
+}
+
+static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
+  const int d = e->dev.d, dr = e->dev.dr, n = e->dev.n, sm = e->sm_count;
+  const bool dense = !e->dev.diag;
+  const bool hconst = P.type == POT_HARMONIC;
+  int ns = 3;
+  if (const char *s = getenv("SC_STREAM_SLOTS")) ns = std::max(2, std::min(4, atoi(s)));
+  StreamLayout L = make_stream_layout(d, dr, 2, ns);
+  while (L.ns > 2 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 2, L.ns - 1);
+  if (sizeof(double) * (size_t)L.total > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "stream pipeline: %zu B of shared memory (d = %d)", sizeof(double) * (size_t)L.total, d);
+  const size_t hsz = (size_t)L.hsz;
+  // constant A operands: [H0 | L1 | L2], padded to d x ldh
+  if (!e->stream_const) CU(cudaMalloc(&e->stream_const, sizeof(double) * 3 * hsz));
+  if (dense && e->stream_h0_src != (const void *)e) {
+    k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L1, dr, d, e->stream_const + hsz, d, L.ldh);
+    k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L2, dr, d, e->stream_const + 2 * hsz, d, L.ldh);
+    CU(cudaGetLastError());
+  }
+  if (hconst) {
+    k_pad_matrix<<<32, 256, 0, st>>>(P.hess0, d, d, e->stream_const, d, L.ldh);
+    CU(cudaGetLastError());
+  }
+  e->stream_h0_src = (const void *)e;
+  int KC = hconst ? 16 : 8;
+  if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
+  {
+    const int npass = (nsteps + KC - 1) / KC;
+    KC = (nsteps + npass - 1) / npass;
+  }
+  const size_t tsz = dense ? (size_t)L.mtr * L.nt * 128 : 0;            // doubles of fragment scratch per matrix
+  const size_t cmsz = (size_t)dr * dr * 2;                               // doubles per prefactor matrix
+  const size_t per_traj = (size_t)KC * sizeof(double) * (cmsz + 2 + 8 + 2 * d + tsz + (hconst ? 0 : 4 * hsz));
+  size_t budget = (size_t)6 << 30;
+  if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
+  long long ntb = (long long)(budget / per_traj);
+  ntb = (ntb / sm) * sm;
+  if (ntb < sm) ntb = sm;
+  if (ntb > n) ntb = n;
+  const size_t need_bytes = per_traj * (size_t)ntb + 1024;
+  if (need_bytes > e->chunk_scratch_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
+    e->chunk_scratch = nullptr;
+    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
+    e->chunk_scratch_cap = need_bytes;
+  }
+  double *base = reinterpret_cast<double *>(e->chunk_scratch);
+  double2 *cm = reinterpret_cast<double2 *>(base);            base += (size_t)KC * ntb * cmsz;
+  double2 *det = reinterpret_cast<double2 *>(base);           base += (size_t)KC * ntb * 2;
+  double *aux = base;                                         base += (size_t)KC * ntb * 8;
+  double *qp = base;                                          base += (size_t)KC * ntb * 2 * d;
+  double *T = dense ? base : nullptr;                         base += (size_t)KC * ntb * tsz;
+  double *hs = hconst ? e->stream_const : base;
+  size_t ngroups = 0;
+  for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
+  if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
+  StreamArgs A;
+  A.hs = hs;
+  A.hs_const = hconst ? 1 : 0;
+  A.L1p = dense ? e->stream_const + hsz : nullptr;
+  A.L2p = dense ? e->stream_const + 2 * hsz : nullptr;
+  A.cm = cm;
+  A.T = T;
+  for (int s0 = 0; s0 < nsteps; s0 += KC) {
+    const int ks = std::min(KC, nsteps - s0);
+    size_t g0 = 0;
+    for (long long t0 = 0; t0 < n; t0 += ntb) {
+      const int nt = (int)std::min<long long>(ntb, n - t0);
+      timing_mark(e, TS_PATH, st);
+      if (P.type == POT_HARMONIC) {
+        const size_t psm = sizeof(double) * ((size_t)d * (d | 1) + PATH_WARPS * ((d + 1) & ~1));
+        CU(cudaFuncSetAttribute(k_path_harmonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k_path_harmonic<<<(nt + PATH_WARPS - 1) / PATH_WARPS, 32 * PATH_WARPS, psm, st>>>(e->dev, P, h, ks, (int)t0, nt, qp, aux);
+      } else {
+        return fail(SC_ERR_UNSUPPORTED, "stream pipeline: potential type %d", P.type);
+      }
+      CU(cudaGetLastError());
+      {
+        const long long items = (long long)ks * nt;
+        const int grid = (int)std::min<long long>((items + 7) / 8, (long long)sm * 8);
+        k_aux_terms<<<grid, 256, 0, st>>>(e->dev, ks, (int)t0, nt, qp, aux);
+        CU(cudaGetLastError());
+      }
+      timing_mark(e, TS_RK4, st);
+      CU(launch_stream(std::min(nt, sm), e->dev, P, h, ks, (int)t0, nt, A, L, st));
+      if (dense) {
+        timing_mark(e, TS_RMULT, st);
+        CU(launch_rmult(e->dev, (long long)ks * nt, T, cm, sm, st));
+      }
+      timing_mark(e, TS_LU, st);
+      CU(launch_lu_batch(cm, dr, ks * nt, det, sm, 0, st));
+      timing_mark(e, TS_FINISH, st);
+      const int nblk = (nt + 127) / 128;
+      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
+      CU(cudaGetLastError());
+      timing_mark(e, TS_END, st);
+      g0 += nblk;
+      e->launches += dense ? 6 : 5;
+    }
+  }
+  k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  e->kernel_name = dense ? (dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_batch+k_hk_finish")
+                         : (dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_batch+k_hk_finish");
   return SC_OK;
 }
 
@@ -685,6 +812,8 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
   if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
   if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && chunk_supported(e->dev, P))
     return run_hk_chunked(e, P, h, nsteps, out_dev, st);
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
+    return run_hk_stream(e, P, h, nsteps, out_dev, st);
   if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;
@@ -1038,22 +1167,33 @@ extern "C" int sc_engine_set_timing(sc_engine *e, int on) {
   return SC_OK;
 }
 
-extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
-  if (!e || !ms4) return fail(SC_ERR_INVALID, "null argument");
+static int timing_collect(sc_engine *e) {
   if (e->tev_used) {
     CU(cudaEventSynchronize(e->tev[e->tev_used - 1]));
     CU(cudaDeviceSynchronize());
-    // per window: 5 marks around k_qp_path, k_rk4_wcols, k_lu_mma, k_hk_finish
-    for (size_t i = 0; i + 4 < e->tev_used; i += 5) {
-      for (int k = 0; k < 4; ++k) {
-        float ms = 0.0f;
-        CU(cudaEventElapsedTime(&ms, e->tev[i + k], e->tev[i + k + 1]));
-        e->tms[k] += ms;
-      }
+    for (size_t i = 0; i + 1 < e->tev_used; ++i) {
+      const int slot = e->tev_slot[i];
+      if (slot < 0 || slot >= SC_TIMING_SLOTS) continue;
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, e->tev[i], e->tev[i + 1]));
+      e->tms[slot] += ms;
     }
     e->tev_used = 0;
   }
+  return SC_OK;
+}
+
+extern "C" int sc_engine_get_timing(sc_engine *e, double *ms4) {
+  if (!e || !ms4) return fail(SC_ERR_INVALID, "null argument");
+  if (int rc = timing_collect(e)) return rc;
   for (int k = 0; k < 4; ++k) ms4[k] = e->tms[k];
+  return SC_OK;
+}
+
+extern "C" int sc_engine_get_timing_slots(sc_engine *e, double *ms, int nslots) {
+  if (!e || !ms) return fail(SC_ERR_INVALID, "null argument");
+  if (int rc = timing_collect(e)) return rc;
+  for (int k = 0; k < nslots; ++k) ms[k] = k < SC_TIMING_SLOTS ? e->tms[k] : 0.0;
   return SC_OK;
 }
 

@@ -370,10 +370,11 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
 
 
 # ------------------------------------------------------------------ general path: dense Gamma, rank deficient
-@pytest.mark.parametrize("d", [23, 40, 54])
+@pytest.mark.parametrize("d", [23, 40, 54, 60, 64])
 def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
-    """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on k_hk_mma in split mode: DMMA prefactor
-    assembly (k-padding at d = 23), batched LU with d' = 17 (k_lu_batch), 34 (k_lu_mma, ragged last panel), 48"""
+    """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on the dense column pipeline (sc_stream.cuh):
+    Hessian and left prefactor factors streamed through the shared-memory ring, k_rmult for the right factors (k-padding at
+    d = 23), batched LU with d' = 17 (k_lu_batch), 34 (k_lu_mma, ragged last panel), 48, 54, 58"""
     from oracle import oracle
     from semiclassical_b200 import workloads, potentials, propagators
     m = workloads.harmonic_molecule_synthetic(d)
@@ -388,7 +389,7 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     pr.set_ensemble(T(m['q0']), T(m['p0']), T(G), T(zi), T(probi))
     a0, i0 = pr.autocorrelation(m['en_zpt']), pr.ic_correlation(pot, m['en_zpt'])
     a, i = pr.propagate(pot, dt, nt - 1, m['en_zpt'])
-    assert pr.kernel_name().startswith("k_hk_mma+")
+    assert pr.kernel_name().startswith("k_rk4_stream+k_rmult+")
     assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
     assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
     pr.step(pot, dt)
