@@ -473,7 +473,7 @@ k_hk_finish(EngDev E, int traj0, int ntb, int nsteps, int step0, int nsteps_tota
 static bool chunk_supported(const EngDev &E, const PotDev &P) {
   if (!E.diag || E.dr != E.d) return false;
   if (P.type != POT_MORSE && P.type != POT_NONHARMONIC) return false;
-  return E.d > 32 && E.d <= 62;   // 63, 64: the set-up / read-out modes of k_hk_generic do not fit in shared memory
+  return E.d > 32 && E.d <= 64;
 }
 
 }  // namespace sc

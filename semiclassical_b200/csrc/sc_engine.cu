@@ -111,7 +111,6 @@ struct sc_engine {
   double tms[SC_TIMING_SLOTS] = {0.0};    // path (+aux), rk4, lu, finish, rmult, potential Hessians
   // dense column pipeline (sc_stream.cuh): padded constant A operands
   double *stream_const = nullptr;         // [H0 | L1 | L2], each d x ldh
-  const void *stream_h0_src = nullptr;    // potential whose Hessian sits in stream_const
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
   long long ntraj_norm = 0;
@@ -642,28 +641,104 @@ __global__ void k_pad_matrix(const double *__restrict__ src, int rows, int cols,
   }
 }
 
+// shared-memory plan of k_rk4_stream and the padded constant A operands [H0 | L1 | L2] (each d x ldh)
+static int stream_setup(sc_engine *e, StreamLayout &L, cudaStream_t st) {
+  const int d = e->dev.d, dr = e->dev.dr;
+  int ns = 3;
+  if (const char *s = getenv("SC_STREAM_SLOTS")) ns = std::max(2, std::min(4, atoi(s)));
+  L = make_stream_layout(d, dr, 2, ns);
+  while (L.ns > 2 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 2, L.ns - 1);
+  if (sizeof(double) * (size_t)L.total > 227 * 1024)
+    return fail(SC_ERR_UNSUPPORTED, "stream pipeline: %zu B of shared memory (d = %d)", sizeof(double) * (size_t)L.total, d);
+  const size_t hsz = (size_t)L.hsz;
+  if (!e->stream_const) {
+    CU(cudaMalloc(&e->stream_const, sizeof(double) * 3 * hsz));
+    if (!e->dev.diag) {
+      k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L1, dr, d, e->stream_const + hsz, d, L.ldh);
+      k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L2, dr, d, e->stream_const + 2 * hsz, d, L.ldh);
+      CU(cudaGetLastError());
+    }
+  }
+  return SC_OK;
+}
+
+static int ensure_chunk_scratch(sc_engine *e, size_t need_bytes, cudaStream_t st) {
+  if (need_bytes > e->chunk_scratch_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
+    e->chunk_scratch = nullptr;
+    e->chunk_scratch_cap = 0;
+    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
+    e->chunk_scratch_cap = need_bytes;
+  }
+  return SC_OK;
+}
+
+// prefactor (+ branch tracking) of the records as they are, for d the generic kernel's MODE_INIT / MODE_TRACK cannot hold in
+// shared memory: k_rk4_stream in its prefactor-only mode -> (k_rmult) -> batched LU -> k_track_only
+static int run_prefactor_stream(sc_engine *e, int mode, cudaStream_t st) {
+  const int d = e->dev.d, dr = e->dev.dr, n = e->dev.n, sm = e->sm_count;
+  const bool dense = !e->dev.diag;
+  StreamLayout L;
+  if (int rc = stream_setup(e, L, st)) return rc;
+  const size_t hsz = (size_t)L.hsz;
+  const size_t tsz = dense ? (size_t)L.mtr * L.nt * 128 : 0, cmsz = (size_t)dr * dr * 2;
+  const size_t per_traj = sizeof(double) * (cmsz + 2 + tsz);
+  long long ntb = (long long)(((size_t)2 << 30) / per_traj);
+  if (ntb > n) ntb = n;
+  if (int rc = ensure_chunk_scratch(e, per_traj * (size_t)ntb + 1024, st)) return rc;
+  double *base = reinterpret_cast<double *>(e->chunk_scratch);
+  double2 *cm = reinterpret_cast<double2 *>(base);            base += (size_t)ntb * cmsz;
+  double2 *det = reinterpret_cast<double2 *>(base);           base += (size_t)ntb * 2;
+  StreamArgs A;
+  A.hs = e->stream_const;
+  A.hs_const = 1;
+  A.L1p = dense ? e->stream_const + hsz : nullptr;
+  A.L2p = dense ? e->stream_const + 2 * hsz : nullptr;
+  A.cm = cm;
+  A.T = dense ? base : nullptr;
+  A.skip_rk4 = 1;
+  PotDev none = PotDev();
+  none.d = d;
+  none.imass = e->dev.q0;
+  for (long long t0 = 0; t0 < n; t0 += ntb) {
+    const int nt = (int)std::min<long long>(ntb, n - t0);
+    CU(launch_stream(std::min(nt, sm), e->dev, none, 0.0, 1, (int)t0, nt, A, L, st));
+    if (dense) CU(launch_rmult(e->dev, nt, A.T, cm, sm, st));
+    CU(launch_lu_batch(cm, dr, nt, det, sm, 0, st));
+    k_track_only<<<(nt + 127) / 128, 128, 0, st>>>(e->dev, (int)t0, nt, det, mode == MODE_INIT ? 1 : 0);
+    CU(cudaGetLastError());
+    e->launches += dense ? 4 : 3;
+  }
+  e->kernel_name = "k_rk4_stream(prefactor)+k_lu+k_track_only";
+  return SC_OK;
+}
+
+// MODE_CORR for d the generic kernel cannot hold: contributions of the current state
+static int run_corr_now(sc_engine *e, double *out_dev, cudaStream_t st) {
+  const int n = e->dev.n;
+  int grid = std::min((n + 7) / 8, e->sm_count * 8);
+  if (grid < 1) grid = 1;
+  if (int rc = ensure_partials(e, (size_t)grid * 5, st)) return rc;
+  k_corr_now<<<grid, 256, 0, st>>>(e->dev, e->partials);
+  CU(cudaGetLastError());
+  k_reduce_partials<<<1, 160, 0, st>>>(e->partials, grid, 1, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
+  CU(cudaGetLastError());
+  e->launches += 2;
+  return SC_OK;
+}
+
 static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
   const int d = e->dev.d, dr = e->dev.dr, n = e->dev.n, sm = e->sm_count;
   const bool dense = !e->dev.diag;
   const bool hconst = P.type == POT_HARMONIC;
-  int ns = 3;
-  if (const char *s = getenv("SC_STREAM_SLOTS")) ns = std::max(2, std::min(4, atoi(s)));
-  StreamLayout L = make_stream_layout(d, dr, 2, ns);
-  while (L.ns > 2 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 2, L.ns - 1);
-  if (sizeof(double) * (size_t)L.total > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "stream pipeline: %zu B of shared memory (d = %d)", sizeof(double) * (size_t)L.total, d);
+  StreamLayout L;
+  if (int rc = stream_setup(e, L, st)) return rc;
   const size_t hsz = (size_t)L.hsz;
-  // constant A operands: [H0 | L1 | L2], padded to d x ldh
-  if (!e->stream_const) CU(cudaMalloc(&e->stream_const, sizeof(double) * 3 * hsz));
-  if (dense && e->stream_h0_src != (const void *)e) {
-    k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L1, dr, d, e->stream_const + hsz, d, L.ldh);
-    k_pad_matrix<<<32, 256, 0, st>>>(e->dev.L2, dr, d, e->stream_const + 2 * hsz, d, L.ldh);
-    CU(cudaGetLastError());
-  }
   if (hconst) {
     k_pad_matrix<<<32, 256, 0, st>>>(P.hess0, d, d, e->stream_const, d, L.ldh);
     CU(cudaGetLastError());
   }
-  e->stream_h0_src = (const void *)e;
   int KC = hconst ? 16 : 8;
   if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
   {
@@ -679,14 +754,7 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   ntb = (ntb / sm) * sm;
   if (ntb < sm) ntb = sm;
   if (ntb > n) ntb = n;
-  const size_t need_bytes = per_traj * (size_t)ntb + 1024;
-  if (need_bytes > e->chunk_scratch_cap) {
-    CU(cudaStreamSynchronize(st));
-    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
-    e->chunk_scratch = nullptr;
-    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
-    e->chunk_scratch_cap = need_bytes;
-  }
+  if (int rc = ensure_chunk_scratch(e, per_traj * (size_t)ntb + 1024, st)) return rc;
   double *base = reinterpret_cast<double *>(e->chunk_scratch);
   double2 *cm = reinterpret_cast<double2 *>(base);            base += (size_t)KC * ntb * cmsz;
   double2 *det = reinterpret_cast<double2 *>(base);           base += (size_t)KC * ntb * 2;
@@ -704,6 +772,7 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   A.L2p = dense ? e->stream_const + 2 * hsz : nullptr;
   A.cm = cm;
   A.T = T;
+  A.skip_rk4 = 0;
   for (int s0 = 0; s0 < nsteps; s0 += KC) {
     const int ks = std::min(KC, nsteps - s0);
     size_t g0 = 0;
@@ -814,6 +883,11 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
     return run_hk_chunked(e, P, h, nsteps, out_dev, st);
   if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
     return run_hk_stream(e, P, h, nsteps, out_dev, st);
+  if (e->dev.d > 62) {                       // the set-up / read-out modes of k_hk_generic do not fit in shared memory
+    if (mode == MODE_INIT || mode == MODE_TRACK) return run_prefactor_stream(e, mode, st);
+    if (mode == MODE_CORR) return run_corr_now(e, out_dev, st);
+    return fail(SC_ERR_UNSUPPORTED, "no fused step kernel for this potential at d = %d; use the stage interface", e->dev.d);
+  }
   if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;

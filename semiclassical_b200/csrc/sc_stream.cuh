@@ -66,6 +66,7 @@ struct StreamArgs {
   const double *L1p, *L2p;       // dense widths: left factors padded to d x ldh (zero rows >= dr), else null
   double2 *cm;                   // diagonal widths: prefactor matrices (step, tl, d, d)
   double *T;                     // dense widths: (step, tl, row tile, column tile, plane, 32 lanes x 2) fragments of L1 U', L2 V'
+  int skip_rk4;                  // 1: prefactor matrices of the records as they are (one "step", no propagation, no write back)
 };
 
 // ------------------------------------------------------------------ matrix kernel
@@ -77,14 +78,15 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   constexpr int NWARP = (NK + NTW - 1) / NTW;
   constexpr int SLAB = DK * 8, SLAB2 = SLAB / 2;
   constexpr int MAXS = 4;
-  extern __shared__ __align__(128) double smem[];
+  extern __shared__ __align__(16) double smem[];
   __shared__ __align__(8) uint64_t full[MAXS];
   __shared__ int cnt[MAXS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int d = E.d, dp = (d + 1) & ~1, dr = E.dr;
   const int NS = L.ns, hsz = L.hsz;
   const bool dense = A.T != nullptr;
-  const int nstg = dense ? 6 : 4;
+  const int nrk = A.skip_rk4 ? 0 : 4;
+  const int nstg = nrk + (dense ? 2 : 0);
   double *ring = smem + L.off_ring;
   double *__restrict__ Wreg = smem + L.off_W + warp * L.wstride;     // tile w: U slab at w 2 SLAB, V slab at w 2 SLAB + SLAB
   const double *csa = smem + L.off_c, *cisa = csa + dp, *csb = cisa + dp, *cisb = csb + dp;
@@ -117,10 +119,11 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   const int n_iter = (ntb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int per_traj = nsteps * nstg;
   const long long G = (long long)n_iter * per_traj;
+  const int per_traj_d = per_traj > 0 ? per_traj : 1;
   auto issue = [&](long long g) {                       // one thread: copy of stage g into its slot
     if (g >= G) return;
-    const int it = (int)(g / per_traj), rem = (int)(g - (long long)it * per_traj);
-    const int step = rem / nstg, sidx = rem - step * nstg;
+    const int it = (int)(g / per_traj_d), rem = (int)(g - (long long)it * per_traj_d);
+    const int step = rem / nstg, sidx = rem - step * nstg + (4 - nrk);
     const int tl = (int)blockIdx.x + it * (int)gridDim.x;
     const double *src;
     if (sidx < 4) src = A.hs_const ? A.hs : A.hs + ((size_t)(step * 4 + sidx) * ntb + tl) * hsz;
@@ -217,7 +220,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       double acc[NTW][MT][2];
       const size_t mat = (size_t)step * ntb + tl;
 #pragma unroll 1
-      for (int s = 1; s <= 4; ++s) {
+      for (int s = 1; s <= nrk; ++s) {
         mma_stage(Ub, two, acc);
         // ---- RK4 bookkeeping on the warp's own slabs, stage operand in place
 #pragma unroll
@@ -249,8 +252,6 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
                 Uw[i * 32] = u;
               }
           } else {
-            const double sb = bok[w] ? csb[b[w]] : 0.0, isb = bok[w] ? cisb[b[w]] : 0.0;
-            double2 *out = dense ? nullptr : A.cm + mat * d * d + (size_t)fr * d + (bok[w] ? b[w] : 0);
 #pragma unroll
             for (int i = 0; i < MT; ++i)
               if (i < MT - 1 || last_ok) {
@@ -258,18 +259,29 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
                 cols_phase_b<4>(u, v, cim[8 * i + fr], h, -acc[w][i][0], -acc[w][i][1], R1[w][i], R2[w][i]);
                 Uw[i * 32] = u;
                 Vw[i * 32] = v;
-                // diagonal widths: prefactor-matrix element (propagators.py:969-986) straight from registers:
-                // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
-                if (!dense && bok[w]) {
-                  const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
-                  out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
-                }
               }
           }
         }
         __syncwarp();
       }
-      if (dense) {
+      if (!dense) {
+        // ---- diagonal widths: the warp's 4 columns of the prefactor matrix (propagators.py:969-986) from its slabs:
+        // u = (Mqq, Mqp)[a][b], v = (Mpq, Mpp)[a][b]
+#pragma unroll
+        for (int w = 0; w < NTW; ++w) {
+          if ((w > 0 && !two) || !bok[w]) continue;
+          const double2 *Uw = Uo + w * 2 * SLAB2, *Vw = Uw + SLAB2;
+          const double sb = csb[b[w]], isb = cisb[b[w]];
+          double2 *out = A.cm + mat * d * d + (size_t)fr * d + b[w];
+#pragma unroll
+          for (int i = 0; i < MT; ++i)
+            if (i < MT - 1 || last_ok) {
+              const double2 u = Uw[i * 32], v = Vw[i * 32];
+              const double sa = csa[8 * i + fr], isa = cisa[8 * i + fr];
+              out[(size_t)i * 8 * d] = make_double2(sa * u.x * isb + isa * v.y * sb, -sa * u.y * sb + isa * v.x * isb);
+            }
+        }
+      } else {
         // ---- stages 5, 6: L1 [Mqq|Mqp] and L2 [Mpq|Mpp] of this warp's columns -> fragment scratch of k_rmult
         const int mtr = L.mtr;
 #pragma unroll 1
@@ -289,6 +301,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       }
     }
     // ---- write back
+    if (A.skip_rk4) continue;
 #pragma unroll
     for (int w = 0; w < NTW; ++w) {
       if (bok[w] && (w == 0 || two)) {
@@ -569,6 +582,77 @@ k_aux_terms(EngDev E, int nsteps, int traj0, int ntb, const double *__restrict__
       for (int i = 1; i < 6; ++i) x = (lane == i) ? v[i] : x;
       aux[(size_t)item * 8 + lane] = x;
     }
+  }
+}
+
+// branch tracking without propagation (MODE_INIT / MODE_TRACK of sc_kernels.cuh for d the generic kernel cannot hold)
+__global__ void k_track_only(EngDev E, int traj0, int nt, const double2 *__restrict__ det, int init) {
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= nt) return;
+  const int traj = traj0 + tl;
+  const double2 dtv = det[tl];
+  E.sign[traj] = init ? 1.0 : track_sign(E.sign[traj], E.c2[traj], dtv);
+  E.c2[traj] = dtv;
+  E.c[traj] = csqrt_principal(dtv);
+}
+
+// contributions of the CURRENT state to C_auto and k_ic (MODE_CORR): one warp per trajectory, per-block partial rows
+__global__ void __launch_bounds__(256)
+k_corr_now(EngDev E, double *__restrict__ partials) {
+  __shared__ double sh[8][2 * SC_MAX_DIM];
+  __shared__ double red[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, d = E.d;
+  double *dqv = sh[warp], *dpv = sh[warp] + d;
+  double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int traj = blockIdx.x * 8 + warp; traj < E.n; traj += gridDim.x * 8) {
+    const double *rec = E.rec + (size_t)traj * E.rs;
+    const double *zt = E.zt + (size_t)traj * 2 * d;
+    __syncwarp();
+    for (int a = lane; a < d; a += 32) { dqv[a] = E.q0[a] - rec[a]; dpv[a] = E.p0[a] - rec[d + a]; }
+    __syncwarp();
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int a = lane; a < d; a += 32) {
+      const double dq = dqv[a], dpa = dpv[a];
+      if (E.diag) {
+        v[0] += -0.5 * (dq * E.otA[a] * dq + dpa * E.otB[a] * dpa);
+        v[1] += -E.p0[a] * dq + dq * E.otC[a] * dpa;
+      } else {
+        double sa = 0.0, sb = 0.0, sc_ = 0.0;
+        for (int j = 0; j < d; ++j) {
+          sa = fma(__ldg(E.otA + j * d + a), dqv[j], sa);
+          sb = fma(__ldg(E.otB + j * d + a), dpv[j], sb);
+          sc_ = fma(__ldg(E.otC + j * d + a), dqv[j], sc_);
+        }
+        v[0] += -0.5 * (dq * sa + dpa * sb);
+        v[1] += -E.p0[a] * dq + dpa * sc_;
+      }
+      const double wr = E.wR[a], wg = E.wG[a];
+      v[2] += dq * wr;
+      v[3] += -dpa * wg;
+      v[4] += (E.q0[a] - zt[a]) * wr;
+      v[5] += (zt[d + a] - E.p0[a]) * wg;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    if (lane == 0) {
+      double2 ca, ki;
+      corr_finish(E, v, rec[2 * d], E.c[traj], E.sign[traj], E.wvi[traj], ca, ki);
+      acc4[0] += ca.x; acc4[1] += ca.y; acc4[2] += ki.x; acc4[3] += ki.y;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[warp][i] = acc4[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    if (threadIdx.x < 4)
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
   }
 }
 

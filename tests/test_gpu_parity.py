@@ -253,7 +253,7 @@ def test_python_potential_through_stage_interface(name, cuda_device):
 
 
 # ------------------------------------------------------------------ column-chunked headline path
-@pytest.mark.parametrize("d", [33, 40, 51, 60, 62])
+@pytest.mark.parametrize("d", [33, 40, 51, 60, 62, 63, 64])
 def test_chunked_path_against_oracle(d, cuda_device):
     """diagonal-Gamma AS models on the chunked RK4 + batched-LU path (sc_chunk.cuh) vs the C oracle: ragged batch
     (n not a multiple of anything), two launches of KC steps, odd chunk widths (d = 51), 4 chunks (d = 62)"""
