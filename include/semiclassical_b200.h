@@ -171,6 +171,12 @@ int sc_engine_get_timing(sc_engine *eng, double *ms4_host);
 /* all SC_TIMING_SLOTS slots: { path (+ overlap terms), RK4/monodromy, LU, finish, right factors (k_rmult), potential
  * Hessians, 0, 0 } of the column pipelines (propagators.py:645-655 has no counterpart: instrumentation only) */
 int sc_engine_get_timing_slots(sc_engine *eng, double *ms_host, int nslots);
+/* run-time options (no reference counterpart; measurement / diagnostics):
+ *   "dense_engine" = 1  separable potentials (Morse / AS, NonHarmonic) are propagated by the general dense column pipeline
+ *                       (sc_stream.cuh: their diagonal Hessians are expanded to full d x d matrices per stage) instead of
+ *                       the structured pipeline of sc_chunk.cuh -- the configuration roofline figures of the dense engine
+ *                       on the AS model are quoted on */
+int sc_engine_set_option(sc_engine *eng, const char *name, int value);
 /* name of the fused kernel variant the last sc_engine_step dispatched to (diagnostics) */
 const char *sc_engine_kernel_name(const sc_engine *eng);
 

@@ -104,6 +104,7 @@ struct sc_engine {
   void *chunk_scratch = nullptr;   // prefactor matrices, determinants, aux rows of one batch (chunked path)
   size_t chunk_scratch_cap = 0;
   // optional per-kernel timing of the chunked path (CUDA events on the launching stream)
+  bool dense_engine = false;      // separable models through the general dense pipeline (sc_engine_set_option)
   bool timing = false;
   std::vector<cudaEvent_t> tev;
   size_t tev_used = 0;
@@ -747,7 +748,8 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   }
   const size_t tsz = dense ? (size_t)L.mtr * L.nt * 128 : 0;            // doubles of fragment scratch per matrix
   const size_t cmsz = (size_t)dr * dr * 2;                               // doubles per prefactor matrix
-  const size_t per_traj = (size_t)KC * sizeof(double) * (cmsz + 2 + 8 + 2 * d + tsz + (hconst ? 0 : 4 * hsz));
+  const int dp = (d + 1) & ~1;
+  const size_t per_traj = (size_t)KC * sizeof(double) * (cmsz + 2 + 8 + 2 * d + tsz + (hconst ? 0 : 4 * hsz + 4 * dp));
   size_t budget = (size_t)6 << 30;
   if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
   long long ntb = (long long)(budget / per_traj);
@@ -761,7 +763,8 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   double *aux = base;                                         base += (size_t)KC * ntb * 8;
   double *qp = base;                                          base += (size_t)KC * ntb * 2 * d;
   double *T = dense ? base : nullptr;                         base += (size_t)KC * ntb * tsz;
-  double *hs = hconst ? e->stream_const : base;
+  double *hs = hconst ? e->stream_const : base;                 base += hconst ? 0 : (size_t)KC * ntb * 4 * hsz;
+  double *hd = base;                                            // stage diagonals of the potentials whose Hessian is expanded
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
@@ -779,19 +782,32 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
     for (long long t0 = 0; t0 < n; t0 += ntb) {
       const int nt = (int)std::min<long long>(ntb, n - t0);
       timing_mark(e, TS_PATH, st);
+      bool aux_done = false;
       if (P.type == POT_HARMONIC) {
         const size_t psm = sizeof(double) * ((size_t)d * (d | 1) + PATH_WARPS * ((d + 1) & ~1));
         CU(cudaFuncSetAttribute(k_path_harmonic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         k_path_harmonic<<<(nt + PATH_WARPS - 1) / PATH_WARPS, 32 * PATH_WARPS, psm, st>>>(e->dev, P, h, ks, (int)t0, nt, qp, aux);
+      } else if (P.type == POT_ROTATED_MORSE) {
+        const size_t psm = sizeof(double) * ((size_t)d * (d | 1) + PATH_WARPS * 2 * ((d + 1) & ~1));
+        CU(cudaFuncSetAttribute(k_path_rotated, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k_path_rotated<<<(nt + PATH_WARPS - 1) / PATH_WARPS, 32 * PATH_WARPS, psm, st>>>(e->dev, P, h, ks, (int)t0, nt, qp, aux, hd);
+      } else if ((P.type == POT_MORSE || P.type == POT_NONHARMONIC) && e->dev.diag) {
+        k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);      // overlap terms included
+        aux_done = true;
       } else {
         return fail(SC_ERR_UNSUPPORTED, "stream pipeline: potential type %d", P.type);
       }
       CU(cudaGetLastError());
-      {
+      if (!aux_done) {
         const long long items = (long long)ks * nt;
         const int grid = (int)std::min<long long>((items + 7) / 8, (long long)sm * 8);
         k_aux_terms<<<grid, 256, 0, st>>>(e->dev, ks, (int)t0, nt, qp, aux);
         CU(cudaGetLastError());
+      }
+      if (!hconst) {
+        timing_mark(e, TS_POT, st);
+        CU(launch_expand(P, P.type == POT_ROTATED_MORSE ? 1 : 0, ks, nt, hd, hs, sm, st));
+        e->launches += 1;
       }
       timing_mark(e, TS_RK4, st);
       CU(launch_stream(std::min(nt, sm), e->dev, P, h, ks, (int)t0, nt, A, L, st));
@@ -879,9 +895,9 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
                          bool allow_mma = true) {
   LaunchPlan pl;
   if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
-  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && chunk_supported(e->dev, P))
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && !e->dense_engine && !getenv("SC_DENSE_ENGINE") && chunk_supported(e->dev, P))
     return run_hk_chunked(e, P, h, nsteps, out_dev, st);
-  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P, e->dense_engine || getenv("SC_DENSE_ENGINE")))
     return run_hk_stream(e, P, h, nsteps, out_dev, st);
   if (e->dev.d > 62) {                       // the set-up / read-out modes of k_hk_generic do not fit in shared memory
     if (mode == MODE_INIT || mode == MODE_TRACK) return run_prefactor_stream(e, mode, st);
@@ -1230,6 +1246,13 @@ extern "C" int sc_engine_wavefunction(sc_engine *e, const double *Gt_host, doubl
   CU(cudaStreamSynchronize(st));
   e->launches += 4;
   return SC_OK;
+}
+
+// run-time options of an engine (diagnostics / measurement; defaults are the production dispatch)
+extern "C" int sc_engine_set_option(sc_engine *e, const char *name, int value) {
+  if (!e || !name) return fail(SC_ERR_INVALID, "null argument");
+  if (std::strcmp(name, "dense_engine") == 0) { e->dense_engine = value != 0; return SC_OK; }
+  return fail(SC_ERR_INVALID, "unknown option '%s'", name);
 }
 
 // per-kernel timing of the chunked path: enable, run sc_engine_step*, then read the accumulated milliseconds

@@ -534,6 +534,223 @@ k_path_harmonic(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, do
   if (lane == 0) rec[2 * d] = S;
 }
 
+// rotated Morse potential (dense parity fixture): V'(x) = V(Q^T x); r = Q^T x, inner Morse per mode,
+// grad = Q g.  One warp per trajectory; the inner second derivatives h_k of every stage go to hd (step, tl, 4, dp) --
+// k_expand_hessian forms H_s = Q diag(h_s) Q^T on the tensor pipe.  Q in shared memory with an odd leading dimension
+// (column access: consecutive lanes; row access: stride ldq).
+__global__ void __launch_bounds__(32 * PATH_WARPS)
+k_path_rotated(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double *__restrict__ qp, double *__restrict__ aux,
+               double *__restrict__ hd) {
+  extern __shared__ __align__(16) double psm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int d = E.d, ldq = d | 1, dp = (d + 1) & ~1;
+  double *Qs = psm, *xv = psm + d * ldq + warp * 2 * dp, *gv = xv + dp;
+  for (int i = t; i < d * d; i += blockDim.x) Qs[(i / d) * ldq + (i % d)] = P.Q[i];
+  __syncthreads();
+  const int tl = blockIdx.x * PATH_WARPS + warp;
+  if (tl >= ntb) return;
+  const int traj = traj0 + tl;
+  double *rec = E.rec + (size_t)traj * E.rs;
+  double q[PATH_NE], p[PATH_NE], im[PATH_NE], pa_[PATH_NE], pD[PATH_NE], pw2[PATH_NE];
+#pragma unroll
+  for (int k = 0; k < PATH_NE; ++k) {
+    const int a = lane + 32 * k;
+    const bool ok = a < d;
+    q[k] = ok ? rec[a] : 0.0;
+    p[k] = ok ? rec[d + a] : 0.0;
+    im[k] = ok ? P.imass[a] : 0.0;
+    pa_[k] = (ok && !P.all_harmonic) ? P.a[a] : 0.0;
+    pD[k] = (ok && !P.all_harmonic) ? P.D[a] : 0.0;
+    pw2[k] = ok ? P.omega[a] * P.omega[a] : 0.0;
+  }
+  double S = rec[2 * d];
+  for (int step = 0; step < nsteps; ++step) {
+    double qs[PATH_NE], ps[PATH_NE], accq[PATH_NE], accp[PATH_NE];
+    double accS = 0.0, e4 = 0.0;
+#pragma unroll
+    for (int k = 0; k < PATH_NE; ++k) { qs[k] = q[k]; ps[k] = p[k]; accq[k] = accp[k] = 0.0; }
+    double *hrow = hd + ((size_t)step * ntb + tl) * 4 * dp;
+#pragma unroll 1
+    for (int s = 1; s <= 4; ++s) {
+      const double cnext = (s == 3) ? h : 0.5 * h;
+      const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
+#pragma unroll
+      for (int k = 0; k < PATH_NE; ++k) {
+        const int a = lane + 32 * k;
+        if (a < d) xv[a] = qs[k];
+      }
+      __syncwarp();
+      double vsum = (lane == 0) ? -P.origin : 0.0;
+#pragma unroll
+      for (int k = 0; k < PATH_NE; ++k) {
+        const int m = lane + 32 * k;
+        if (m < d) {
+          double r = 0.0;
+          for (int i = 0; i < d; ++i) r = fma(Qs[i * ldq + m], xv[i], r);
+          double gi, hi;
+          if (P.all_harmonic) {
+            vsum += 0.5 * pw2[k] * r * r;
+            gi = pw2[k] * r;
+            hi = pw2[k];
+          } else {
+            const double e = exp(-pa_[k] * r);
+            vsum += pD[k] * (1.0 - e) * (1.0 - e);
+            gi = 2.0 * pa_[k] * pD[k] * e * (1.0 - e);
+            hi = 2.0 * pa_[k] * pa_[k] * pD[k] * e * (2.0 * e - 1.0);
+          }
+          gv[m] = gi;
+          hrow[(s - 1) * dp + m] = hi;
+        }
+      }
+      __syncwarp();
+      double tv = -vsum, te = vsum;
+#pragma unroll
+      for (int k = 0; k < PATH_NE; ++k) {
+        const int a = lane + 32 * k;
+        if (a < d) {
+          const double *qr = Qs + a * ldq;
+          double g = 0.0;
+          for (int m = 0; m < d; ++m) g = fma(qr[m], gv[m], g);
+          const double kq = ps[k] * im[k], kp = -g;
+          const double tk = 0.5 * ps[k] * ps[k] * im[k];
+          tv += tk;
+          te += tk;
+          accq[k] += wgt * kq;
+          accp[k] += wgt * kp;
+          if (s < 4) {
+            qs[k] = q[k] + cnext * kq;
+            ps[k] = p[k] + cnext * kp;
+          }
+        }
+      }
+      accS += wgt * tv;
+      if (s == 4) e4 = te;
+      __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      accS += __shfl_xor_sync(0xffffffffu, accS, o);
+      e4 += __shfl_xor_sync(0xffffffffu, e4, o);
+    }
+    S += h / 6.0 * accS;
+    double *qo = qp + ((size_t)step * ntb + tl) * 2 * d;
+#pragma unroll
+    for (int k = 0; k < PATH_NE; ++k) {
+      const int a = lane + 32 * k;
+      q[k] += h / 6.0 * accq[k];
+      p[k] += h / 6.0 * accp[k];
+      if (a < d) { qo[a] = q[k]; qo[d + a] = p[k]; }
+    }
+    if (lane == 0) {
+      double *ax = aux + ((size_t)step * ntb + tl) * 8;
+      ax[6] = S;
+      ax[7] = e4;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PATH_NE; ++k) {
+    const int a = lane + 32 * k;
+    if (a < d) { rec[a] = q[k]; rec[d + a] = p[k]; }
+  }
+  if (lane == 0) rec[2 * d] = S;
+}
+
+// Hessian stream images (d x LDH, zero padded) from the stage diagonals hd (item, dp), item = (step, tl, stage):
+//   ROT = 0  H = diag(h)                    (separable models run through the general dense engine)
+//   ROT = 1  H = Q diag(h) Q^T              (rotated Morse fixture) on the tensor pipe: A fragment = Q[i][k] h[k], B fragment =
+//            Q[j][k], upper-triangular 8 x 8 tiles + mirrored stores.  Q in shared memory, ld = LDH (conflict-free fragments)
+// The image of item (step, tl, s) goes to hs + ((step 4 + s) ntb + tl) hsz.
+template <int NK, int ROT>
+__global__ void __launch_bounds__(256)
+k_expand_hessian(PotDev P, int nsteps, int ntb, const double *__restrict__ hd, double *__restrict__ hs) {
+  constexpr int MT = (NK + 1) / 2, LDH = cols_ldh(NK);
+  extern __shared__ __align__(16) double esm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int d = P.d, dp = (d + 1) & ~1, hsz = d * LDH;
+  const int fr = lane >> 2, fc = lane & 3;
+  double *Qs = esm, *hv = esm + (ROT ? 8 * MT * LDH : 0) + warp * 4 * NK;
+  if (ROT) {
+    for (int i = t; i < 8 * MT * LDH; i += blockDim.x) {
+      const int r = i / LDH, c = i - r * LDH;
+      Qs[i] = (r < d && c < d) ? P.Q[r * d + c] : 0.0;
+    }
+    __syncthreads();
+  }
+  const long long nitems = (long long)nsteps * ntb * 4;
+  for (long long item = (long long)blockIdx.x * 8 + warp; item < nitems; item += (long long)gridDim.x * 8) {
+    const long long st_tl = item >> 2;
+    const int s = (int)(item & 3), step = (int)(st_tl / ntb), tl = (int)(st_tl - (long long)step * ntb);
+    const double *hrow = hd + (size_t)item * dp;
+    double *H = hs + ((size_t)(step * 4 + s) * ntb + tl) * hsz;
+    if (!ROT) {
+      for (int i = lane; i < hsz; i += 32) {
+        const int r = i / LDH, c = i - r * LDH;
+        H[i] = (r == c) ? hrow[r] : 0.0;
+      }
+      continue;
+    }
+    __syncwarp();
+    for (int k = lane; k < 4 * NK; k += 32) hv[k] = k < d ? hrow[k] : 0.0;
+    __syncwarp();
+    // zero padding columns d .. LDH - 1
+    for (int i = lane; i < d * (LDH - d); i += 32) {
+      const int r = i / (LDH - d), c = d + i - r * (LDH - d);
+      H[r * LDH + c] = 0.0;
+    }
+#pragma unroll 1
+    for (int I = 0; I < MT; ++I) {
+      double a[NK];
+#pragma unroll
+      for (int kk = 0; kk < NK; ++kk) a[kk] = Qs[(8 * I + fr) * LDH + 4 * kk + fc] * hv[4 * kk + fc];
+#pragma unroll 1
+      for (int J = I; J < MT; ++J) {
+        double c0 = 0.0, c1 = 0.0;
+        const double *bq = Qs + (8 * J + fr) * LDH + fc;
+#pragma unroll
+        for (int kk = 0; kk < NK; ++kk) dmma884(c0, c1, a[kk], bq[4 * kk]);
+        const int row = 8 * I + fr, col = 8 * J + 2 * fc;
+        if (row < d) {
+          if (col < d) H[row * LDH + col] = c0;
+          if (col + 1 < d) H[row * LDH + col + 1] = c1;
+        }
+        if (J > I && row < d) {
+          if (col < d) H[col * LDH + row] = c0;
+          if (col + 1 < d) H[(col + 1) * LDH + row] = c1;
+        }
+      }
+    }
+  }
+}
+
+template <int NK>
+static cudaError_t launch_expand_t(const PotDev &P, int rot, int nsteps, int ntb, const double *hd, double *hs, int sm_count,
+                                   cudaStream_t st) {
+  constexpr int MT = (NK + 1) / 2, LDH = cols_ldh(NK);
+  const long long nitems = (long long)nsteps * ntb * 4;
+  long long grid = std::min<long long>((nitems + 7) / 8, (long long)sm_count * (rot ? 2 : 8));
+  if (grid < 1) grid = 1;
+  if (rot) {
+    const size_t smem = sizeof(double) * ((size_t)8 * MT * LDH + 8 * 4 * NK);
+    cudaError_t ce = cudaFuncSetAttribute(k_expand_hessian<NK, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    k_expand_hessian<NK, 1><<<(int)grid, 256, smem, st>>>(P, nsteps, ntb, hd, hs);
+  } else {
+    k_expand_hessian<NK, 0><<<(int)grid, 256, 0, st>>>(P, nsteps, ntb, hd, hs);
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_expand(const PotDev &P, int rot, int nsteps, int ntb, const double *hd, double *hs, int sm_count,
+                                 cudaStream_t st) {
+  switch ((P.d + 3) / 4) {
+#define SC_EXPAND_CASE(N) case N: return launch_expand_t<N>(P, rot, nsteps, ntb, hd, hs, sm_count, st);
+    SC_EXPAND_CASE(5) SC_EXPAND_CASE(6) SC_EXPAND_CASE(7) SC_EXPAND_CASE(8) SC_EXPAND_CASE(9) SC_EXPAND_CASE(10)
+    SC_EXPAND_CASE(11) SC_EXPAND_CASE(12) SC_EXPAND_CASE(13) SC_EXPAND_CASE(14) SC_EXPAND_CASE(15) SC_EXPAND_CASE(16)
+#undef SC_EXPAND_CASE
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // overlap / NAC partial sums v[0..5] (corr_terms, sc_device.cuh) of every (step, trajectory) from the stored q, p; one warp
 // per item, dense or diagonal overlap matrices
 __global__ void __launch_bounds__(256)
@@ -656,9 +873,12 @@ k_corr_now(EngDev E, double *__restrict__ partials) {
   }
 }
 
-static bool stream_supported(const EngDev &E, const PotDev &P) {
+// dense_engine: separable models too (their diagonal Hessians are expanded to full matrices: the kernel multiplies
+// whatever it is given; sc_chunk.cuh is the path that knows about the structure)
+static bool stream_supported(const EngDev &E, const PotDev &P, bool dense_engine) {
   if (E.d < 17 || E.d > 64) return false;
-  return P.type == POT_HARMONIC;
+  if (P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE) return true;
+  return dense_engine && E.diag && E.dr == E.d && (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
 }
 
 }  // namespace sc

@@ -534,6 +534,10 @@ class HermanKlukPropagator(object):
                                                        self._stream()))
         return float(np.sqrt(out[0]))
 
+    def set_option(self, name, value):
+        """engine run-time options (include/semiclassical_b200.h: sc_engine_set_option), e.g. 'dense_engine'"""
+        _native.check(_native.lib().sc_engine_set_option(self._engine, name.encode(), int(value)))
+
     def launch_count(self):
         return int(_native.lib().sc_engine_launch_count(self._engine))
 

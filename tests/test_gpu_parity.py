@@ -399,6 +399,54 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
+@pytest.mark.parametrize("name", ["hk_as24_rot", "hk_as60_rot"])
+def test_rotated_models_run_on_the_stream_pipeline(name, cuda_device):
+    """per-trajectory dense Hessians (Q diag(h) Q^T formed by k_expand_hessian) + dense width matrices: the reference's own
+    goldens of the rotated AS models, on k_rk4_stream"""
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    nt, e0 = int(g['nt']), float(g['energy0_es'])
+    a0, i0 = pr.autocorrelation(e0), pr.ic_correlation(pot, e0)
+    a, i = pr.propagate(pot, float(g['dt']), nt - 1, e0)
+    assert pr.kernel_name().startswith("k_rk4_stream+k_rmult+")
+    assert relerr(np.concatenate(([a0], a)), g['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), g['ic_correlation']) < TOL
+    pr.step(pot, float(g['dt']))
+    nk = g['y_final'].shape[1]
+    assert relerr(pr.y[:, :nk].cpu().numpy(), g['y_final']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
+
+
+@pytest.mark.parametrize("d", [20, 33, 60, 64])
+def test_dense_engine_option_on_separable_model(d, cuda_device):
+    """AS model through the general dense pipeline (diagonal stage Hessians expanded to full matrices, option
+    'dense_engine') vs the C oracle -- the configuration the dense-engine roofline of configs[3] is quoted on"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_synthetic(d)
+    G = np.diag(m.omega)
+    n, nt = 211, 11
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(300 + d))
+    dt, _ = workloads.test_time_grid()
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi, probi,
+                     dt, nt, m.en_zpt)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    pr.set_option("dense_engine", 1)
+    a0, i0 = pr.autocorrelation(m.en_zpt), pr.ic_correlation(pot, m.en_zpt)
+    a, i = pr.propagate(pot, dt, nt - 1, m.en_zpt)
+    assert pr.kernel_name().startswith("k_rk4_stream+k_lu")
+    assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    ref2 = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi, probi,
+                      dt, nt, m.en_zpt)
+    assert relerr(pr.y.cpu().numpy(), ref2['y']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
+
+
 # ------------------------------------------------------------------ BASELINE size: size-independent properties
 def test_full_size_properties_c4(cuda_device):
     """configs[3] at its full single-GPU size (10^6 trajectories, 60 modes, ~116 GB of state) where no oracle run is
