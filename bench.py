@@ -3,19 +3,29 @@
 bench.py -- headline benchmark of the HK hot path (BASELINE.json: "HK trajectory-steps/sec, AS 60-mode fp64").
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--ntraj NTOTAL] [--dim D] [--dense]
+                    [--dense-engine] [--no-dense-legs] [--no-cpu-baseline]
 
 Workload (configs[3]): synthetic anharmonic AS model, 60 modes, Herman-Kluk propagator,
-10^6 trajectories in total, sharded contiguously over the N ranks (strong scaling: the global ensemble is fixed).
-One "step" = one RK4 time step of every trajectory incl. 4 potential evaluations, the complex LU prefactor with
-branch tracking and the contributions to both correlation functions.  The K timed steps run as ONE fused launch
-(the state of a trajectory stays in shared memory for all K steps); the per-step correlation sums are
-all-reduced over NCCL inside the timed region when N > 1.
+10^6 trajectories in total.  ONE global ensemble is drawn from a fixed seed (identically on every rank) and sharded
+contiguously over the N ranks (strong scaling: the global ensemble is fixed), so `check` is the same at every N.
+One "step" = one RK4 time step of every trajectory incl. 4 potential evaluations, the complex LU prefactor with branch
+tracking and the contributions to both correlation functions.  The K timed steps run as ONE fused launch sequence; the
+per-step correlation sums are all-reduced over NCCL inside the timed region when N > 1.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle port (oracle/sc_oracle.c, OpenMP over all
-host cores) on a bounded sample of the same workload -- the reference itself is pure Python and does not exist on
-the GPU box.
+The JSON line carries
+  roofline        the dominant kernel of the timed region (the structured pipeline of sc_chunk.cuh: H_s = H0 + diag(h_s)
+                  with H0 = 0 for the separable AS model -- labelled as such, it is NOT the dense-engine figure)
+  roofline_dense  (N = 1) the general dense pipeline (sc_stream.cuh) measured in the same run on
+                    as_d60_dense_engine : the same AS ensemble, Hessians expanded to full per-trajectory matrices
+                    harmonic_d60        : dense harmonic molecule-like model, d = 60, d' = 54, dense width matrices
+                    rotated_as_d60      : rotated AS model, per-trajectory dense Hessians + dense width matrices
+  peak            FP64 tensor-pipe peak measured in this run (sc_measure_fp64_peak: DMMA.8x8x4 chains on every SM)
+`--impl reference` times the CPU oracle port (oracle/sc_oracle.c, OpenMP over all host cores) on a bounded sample of
+the same workload -- the reference itself is pure Python and does not exist on the GPU box.
 """
 import argparse
+import ctypes
+import gc
 import json
 import os
 import subprocess
@@ -30,23 +40,20 @@ sys.path.insert(0, ROOT)
 
 from semiclassical_b200 import workloads  # noqa: E402
 
-# DRAM traffic of the dominant kernel per trajectory-step, from the committed `ncu --set full` captures
-# (dram__bytes_read.sum + dram__bytes_write.sum;
-#  profiles/ncu_r01_f_k_rk4_wcols.txt: one launch of 9 768 trajectories x 10 steps)
-TRAFFIC_BYTES_PER_TRAJ_STEP = {"k_rk4_wcols": (1528.7e6 + 7494.6e6) / 97680.0}
-FLOP_PER_TRAJ_STEP = lambda d, dr, dense: 16.0 * d**3 + (8.0 / 3.0) * dr**3 + (8.0 * dr * d * d + 8.0 * dr * dr * d if dense else 0.0)  # noqa: E731
+
+def flop_per_traj_step(d, dr, dense_gamma):
+    """algorithmic flops: RK4 16 d^3, LU 8/3 d'^3, dense widths + 8 d' d^2 + 8 d'^2 d"""
+    return 16.0 * d**3 + (8.0 / 3.0) * dr**3 + ((8.0 * dr * d * d + 8.0 * dr * dr * d) if dense_gamma else 0.0)
 
 
-def fp64_peak_tflops():
-    """FP64 roofline denominator: MEASURED_PEAKS.json has no fp64 entry, so the DMMA/DFMA microbenchmark of
-    tools/fp64_peak.cu measured on this pool's B200 (profiles/fp64_peak_r01.json) is used"""
-    path = os.path.join(ROOT, "profiles", "fp64_peak_r01.json")
+def load_traffic():
+    """DRAM bytes per trajectory-step of the matrix kernels from the committed `ncu --set full` captures
+    (dram__bytes_read.sum + dram__bytes_write.sum / trajectory-steps of the captured launch), profiles/traffic_r02.json"""
     try:
-        with open(path) as f:
-            j = json.load(f)
-        return max(v for k, v in j.items() if k.startswith("dmma884_tflops")), "profiles/fp64_peak_r01.json (tools/fp64_peak.cu, DMMA.8x8x4 register-resident)"
+        with open(os.path.join(ROOT, "profiles", "traffic_r02.json")) as f:
+            return json.load(f)
     except Exception:
-        return 37.0, "nominal B200 FP64 (fallback, microbenchmark file missing)"
+        return {}
 
 
 class ClockSampler(object):
@@ -98,8 +105,9 @@ def build_model(dim, dense):
     return model, G, Q, q0, p0
 
 
-def cpu_run(model, G, Q, q0, p0, ntraj, nsteps, nthreads=0, seed=0):
-    """time the oracle port on `ntraj` trajectories x `nsteps` steps; returns (traj-steps/s, threads)"""
+def cpu_run(model, G, Q, q0, p0, ntraj, nsteps, seed=0):
+    """time the oracle port on `ntraj` trajectories x `nsteps` steps with ALL host cores (explicit thread count: torchrun
+    exports OMP_NUM_THREADS=1); returns (traj-steps/s, threads, seconds)"""
     from oracle import oracle
     if Q is None:
         pot = oracle.Potential.morse(model.omega, model.chi, model.nac)
@@ -108,8 +116,9 @@ def cpu_run(model, G, Q, q0, p0, ntraj, nsteps, nthreads=0, seed=0):
     consts = oracle.Consts(G, G, G, q0, p0)
     zi, probi = oracle.sample_ensemble(G, G, q0, p0, ntraj, np.random.default_rng(seed))
     dt, _ = workloads.test_time_grid()
+    ncpu = os.cpu_count() or 1
     t0 = time.perf_counter()
-    oracle.run(pot, consts, zi, probi, dt, nsteps, model.en_zpt, nthreads=nthreads, want_state=False)
+    oracle.run(pot, consts, zi, probi, dt, nsteps, model.en_zpt, nthreads=ncpu, want_state=False)
     el = time.perf_counter() - t0
     return ntraj * nsteps / el, oracle.lib().sc_oracle_num_threads(), el
 
@@ -123,6 +132,9 @@ def main():
     ap.add_argument("--ntraj", type=int, default=1000000, help="global ensemble size")
     ap.add_argument("--dim", type=int, default=60)
     ap.add_argument("--dense", action="store_true", help="rotated AS model: dense Hessian and dense Gamma")
+    ap.add_argument("--dense-engine", action="store_true", help="AS model through the general dense pipeline (sc_stream.cuh)")
+    ap.add_argument("--no-dense-legs", action="store_true", help="skip the roofline_dense legs")
+    ap.add_argument("--dense-ntraj", type=int, default=148000, help="ensemble of the harmonic / rotated roofline_dense legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mma", action="store_true", help="force the DFMA kernel (diagnostics)")
     args = ap.parse_args()
@@ -138,7 +150,7 @@ def main():
     workload = f"synthetic anharmonic AS model, {d} modes, HK, {args.ntraj} trajectories" + (" (rotated: dense Hessian/Gamma)" if args.dense else "")
     config = {"workload": workload, "ntraj_global": args.ntraj, "dim": d, "dt_au": workloads.test_time_grid()[0],
               "potential": "rotated_morse" if args.dense else "morse", "gamma": "dense" if args.dense else "diag(omega)",
-              "sharding": f"{world} rank(s), contiguous trajectory slices",
+              "sharding": f"{world} rank(s), contiguous slices of ONE global ensemble (seed 1234)",
               "l2": "state (>=116 KB/trajectory) far exceeds the 126 MB L2; no flush needed"}
     metric, unit = "HK trajectory-steps/sec, AS 60-mode fp64", "trajectory-steps/s"
 
@@ -147,16 +159,18 @@ def main():
         if rank != 0:
             return
         n_s = 1024 if d >= 32 else 8192
+        ns = 10                                     # time steps per bench step: the t = 0 prefactor is amortised as in a real run
         times = []
-        for _ in range(W):
-            cpu_run(model, G, Q, q0, p0, n_s, 1)
+        for _ in range(min(W, 1)):
+            cpu_run(model, G, Q, q0, p0, n_s, ns)
         t_all0 = time.perf_counter()
+        cores = 1
         for _ in range(K):
-            v, cores, el = cpu_run(model, G, Q, q0, p0, n_s, 1)
+            v, cores, el = cpu_run(model, G, Q, q0, p0, n_s, ns)
             times.append(el)
         total = time.perf_counter() - t_all0
-        value = n_s * K / sum(times)
-        sample = f"{n_s} trajectories x 1 time step per bench step (bounded sample of the {args.ntraj}-trajectory workload)"
+        value = n_s * ns * K / sum(times)
+        sample = f"{n_s} trajectories x {ns} time steps per bench step (bounded sample of the {args.ntraj}-trajectory workload), {cores} OpenMP threads"
         line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * sum(times) / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": config,
@@ -177,31 +191,79 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    from semiclassical_b200 import potentials, propagators
+    from semiclassical_b200 import _native, distributed, potentials, propagators
 
     T = lambda x: torch.from_numpy(np.ascontiguousarray(x))  # noqa: E731
+    st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     n_total = args.ntraj
-    from semiclassical_b200 import distributed
     lo, hi = distributed.shard_bounds(n_total, rank, world)
     n_local = hi - lo
+    dt = workloads.test_time_grid()[0]
+    if args.no_mma:
+        os.environ["SC_NO_MMA"] = "1"
+
+    # FP64 roofline denominator, measured now on this device
+    pk = np.zeros(2)
+    _native.check(_native.lib().sc_measure_fp64_peak(pk.ctypes.data, 3, st))
+    peak, peak_src = float(pk[0]), ("measured in this run: sc_measure_fp64_peak (DMMA.8x8x4 register-resident chains on every SM, best of 3; "
+                                    f"DFMA chains: {pk[1]:.2f} TFLOP/s); MEASURED_PEAKS.json has no FP64 entry")
+
+    def timed_leg(pr, pot, e_zpt, nsteps, dr, dense_gamma, label):
+        """K fused steps with per-kernel CUDA-event timing on the launching stream -> roofline block"""
+        handle = pot._handle(device)
+        _native.check(_native.lib().sc_engine_set_timing(pr._engine, 1))
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        _native.check(_native.lib().sc_engine_step_dev(pr._engine, handle, dt, nsteps, None, st))
+        e5.record()
+        torch.cuda.synchronize()
+        ms_all = e4.elapsed_time(e5)
+        kt = np.zeros(8)
+        _native.check(_native.lib().sc_engine_get_timing_slots(pr._engine, kt.ctypes.data, 8))
+        _native.check(_native.lib().sc_engine_set_timing(pr._engine, 0))
+        pr.t = pr.t + nsteps * dt
+        dd, n = pr.dim, pr.ntraj
+        kname = pr.kernel_name()
+        flop = flop_per_traj_step(dd, dr, dense_gamma)
+        ach_step = flop * n * nsteps / (ms_all * 1e-3) / 1e12
+        # dominant kernel: the RK4 / monodromy kernel; k_rk4_stream also carries the left factors of a dense prefactor
+        dom_flop = 16.0 * dd**3 + (8.0 * dr * dd * dd if (dense_gamma and kname.startswith("k_rk4_stream")) else 0.0)
+        dom_ms = float(kt[1]) if kt[1] > 0.0 else ms_all
+        if kt[1] <= 0.0:
+            dom_flop = flop
+        ach = dom_flop * n * nsteps / (dom_ms * 1e-3) / 1e12
+        tr = load_traffic().get(kname.split("+")[0])
+        return {"label": label, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": (tr["bytes_per_trajectory_step"] * n * nsteps) if tr else None,
+                "traffic_source": tr.get("capture") if tr else None,
+                "kernel": kname.split("+")[0], "kernel_ms": dom_ms, "flop_per_trajectory_step": dom_flop,
+                "trajectories": n, "steps": nsteps, "traj_steps_per_s": n * nsteps / (ms_all * 1e-3),
+                "whole_step": {"achieved": ach_step, "frac": ach_step / peak, "ms": ms_all, "flop_per_trajectory_step": flop,
+                               "kernels": kname,
+                               "kernel_ms": {"path_and_overlap_terms": float(kt[0]), "potential_hessians": float(kt[5]), "rk4": float(kt[1]),
+                                             "rmult": float(kt[4]), "lu": float(kt[2]), "finish": float(kt[3])}}}
+
     if Q is None:
         pot = potentials.MorsePotential(T(model.omega), T(model.chi), T(model.nac))
     else:
         pot = potentials.RotatedMorsePotential(T(model.omega), T(model.chi), T(model.nac), T(Q))
-    dt = workloads.test_time_grid()[0]
-    if args.no_mma:
-        os.environ["SC_NO_MMA"] = "1"
     pr = propagators.HermanKlukPropagator(T(G), T(G), device=device)
-    # every rank samples its own shard with the propagator's sampler (initial_conditions); the shard is then kept in
-    # pinned host memory so that the end-to-end leg starts from host buffers
-    torch.manual_seed(1234 + rank)
-    pr.initial_conditions(T(q0), T(p0), T(G), ntraj=n_local, ntraj_total=n_total)
-    zi_pin, probi_pin = pr.zi.cpu().pin_memory(), pr.probi.cpu().pin_memory()
+    # ONE global ensemble from a fixed seed, drawn identically on every rank; each rank keeps its contiguous slice in pinned
+    # host memory so that the end-to-end leg starts from host buffers
+    torch.manual_seed(1234)
+    zi_g, probi_g = pr.sample_ensemble(T(q0), T(p0), T(G), n_total)
+    zi_pin, probi_pin = zi_g[:, lo:hi].contiguous().cpu().pin_memory(), probi_g[lo:hi].contiguous().cpu().pin_memory()
+    del zi_g, probi_g
+    torch.cuda.empty_cache()
     ens_bytes = zi_pin.numel() * 8 + probi_pin.numel() * 8
 
     def install():
         pr.set_ensemble(T(q0), T(p0), T(G), zi_pin.to(device, non_blocking=True), probi_pin.to(device, non_blocking=True),
                         ntraj_total=n_total)
+
+    install()
+    if args.dense_engine:
+        pr.set_option("dense_engine", 1)
 
     def run_steps(nsteps):
         # K fused steps; for N > 1 the (K, 5) buffer of per-step sums is all-reduced on the device (NCCL) before
@@ -239,14 +301,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.time()
     e0.record()
-    auto, ic = run_steps(K)
+    run_steps(K)
     e1.record()
     barrier()
-    tw1 = time.time()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = pr.launch_count() - l0
     value = n_total * K / (ms * 1e-3)
-    # ---- timed region 2 (e2e): host buffers -> device, K steps, correlation functions back on the host
+    # ---- timed region 2 (e2e): host buffers -> device, K steps, correlation functions back on the host.  It restarts from
+    # the ensemble at t = 0, so its correlation functions are a property of the global ensemble alone (`check`)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -256,60 +318,97 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     clocks = sampler.stop(tw0, time.time()) if rank == 0 else None
-    # ---- kernel-only duration of the dominant kernel, CUDA events on the launching stream
+    # ---- kernel-only durations, CUDA events on the launching stream
     barrier()
-    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    from semiclassical_b200 import _native
-    import ctypes
-    st = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-    handle = pot._handle(device)
-    _native.check(_native.lib().sc_engine_set_timing(pr._engine, 1))
-    e4.record()
-    _native.check(_native.lib().sc_engine_step_dev(pr._engine, handle, dt, K, None, st))
-    e5.record()
-    torch.cuda.synchronize()
-    ms_kernel = e4.elapsed_time(e5)
-    kt = np.zeros(4)
-    _native.check(_native.lib().sc_engine_get_timing(pr._engine, kt.ctypes.data))
-    _native.check(_native.lib().sc_engine_set_timing(pr._engine, 0))
-    pr.t = pr.t + K * dt
-    flop = FLOP_PER_TRAJ_STEP(d, d, args.dense)
-    peak, peak_src = fp64_peak_tflops()
-    achieved_step = flop * n_local * K / (ms_kernel * 1e-3) / 1e12
-    if kt[1] > 0.0:
-        # column-chunked path: the dominant kernel is the RK4/monodromy kernel (16 d^3 of the 16 d^3 + 8/3 d^3 flops)
-        dom_kernel, dom_ms, dom_flop = pr.kernel_name().split("+")[0], float(kt[1]), 16.0 * d**3
+    dense_gamma = args.dense
+    if args.dense or args.dense_engine:
+        label = "general dense pipeline (sc_stream.cuh)"
     else:
-        dom_kernel, dom_ms, dom_flop = pr.kernel_name(), ms_kernel, flop
-    achieved = dom_flop * n_local * K / (dom_ms * 1e-3) / 1e12
+        label = ("structured pipeline (sc_chunk.cuh): H_s = H0 + diag(h_s), dense base H0 multiplied in full on DMMA but identically "
+                 "ZERO for the separable AS model -- the rate of the instruction stream, NOT a dense-engine figure (see roofline_dense)")
+    roof = timed_leg(pr, pot, model.en_zpt, K, d, dense_gamma, label)
+    roofline_dense = None
+    if world == 1 and not args.no_dense_legs and not args.dense and d >= 17:
+        roofline_dense = {}
+        if not args.dense_engine:
+            # (i) the same ensemble, same model, through the general dense engine
+            pr.set_option("dense_engine", 1)
+            run_steps(K)
+            roofline_dense["as_d%d_dense_engine" % d] = timed_leg(
+                pr, pot, model.en_zpt, K, d, False,
+                "configs[3] ensemble on the general dense pipeline: per-trajectory stage Hessians expanded to full d x d matrices and "
+                "streamed; the kernel does not know they are diagonal")
+            pr.set_option("dense_engine", 0)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
+    if roofline_dense is not None:
+        del pr
+        gc.collect()
+        torch.cuda.empty_cache()
+        nd = args.dense_ntraj
+        # (ii) dense harmonic molecule-like model: dense constant Hessian, dense rank-deficient width matrices (d' = d - 6)
+        hm = workloads.harmonic_molecule_synthetic(d)
+        hpot = potentials.MolecularHarmonicPotential.from_arrays(hm['pos0'], hm['energy0'], hm['grad0'], hm['hess0'], hm['masses'], hm['nac'])
+        hpr = propagators.HermanKlukPropagator(T(hm['Gamma_0']), T(hm['Gamma_0']), device=device)
+        torch.manual_seed(4321)
+        hpr.initial_conditions(T(hm['q0']), T(hm['p0']), T(hm['Gamma_0']), ntraj=nd)
+        hpr.propagate(hpot, dt, K, hm['en_zpt'])
+        roofline_dense["harmonic_d%d" % d] = timed_leg(
+            hpr, hpot, hm['en_zpt'], K, d - 6, True,
+            "workloads.harmonic_molecule_synthetic: dense Hessian (constant, streamed from one copy), dense width matrices with 6 zero modes")
+        del hpr
+        gc.collect()
+        torch.cuda.empty_cache()
+        # (iii) rotated AS model: per-trajectory dense Hessians Q diag(h) Q^T and dense width matrices
+        _, Gr, Qr, q0r, p0r = build_model(d, True)
+        rpot = potentials.RotatedMorsePotential(T(model.omega), T(model.chi), T(model.nac), T(Qr))
+        rpr = propagators.HermanKlukPropagator(T(Gr), T(Gr), device=device)
+        torch.manual_seed(4322)
+        rpr.initial_conditions(T(q0r), T(p0r), T(Gr), ntraj=nd)
+        rpr.propagate(rpot, dt, K, model.en_zpt)
+        roofline_dense["rotated_as_d%d" % d] = timed_leg(
+            rpr, rpot, model.en_zpt, K, d, True,
+            "rotated AS model (SURVEY 8c-vi): per-trajectory dense Hessians (formed by k_expand_hessian, not counted as algorithmic "
+            "flops) and dense width matrices")
+        del rpr
+        gc.collect()
+        torch.cuda.empty_cache()
     assert abs(c0 - 1.0) < 1e-3 * max(1.0, 3000.0 / np.sqrt(n_total)), f"C(0) = {c0}"
-    assert np.all(np.isfinite(auto)) and np.all(np.isfinite(ic))
+    assert np.all(np.isfinite(auto2)) and np.all(np.isfinite(ic2))
+    # multi-GPU parity evidence: the e2e leg's correlation functions depend only on the global ensemble (seed 1234), so they
+    # must agree at every N to reduction-order accuracy; profiles/check_r02.json holds the N = 1 values
+    check = {"C0": [c0.real, c0.imag], "auto_last": [auto2[-1].real, auto2[-1].imag], "ic_last": [ic2[-1].real, ic2[-1].imag],
+             "auto_abs_sum": float(np.abs(auto2).sum())}
+    try:
+        with open(os.path.join(ROOT, "profiles", "check_r02.json")) as f:
+            stored = json.load(f).get(f"{'dense' if args.dense else 'as'}_d{d}_n{n_total}_k{K}")
+        if stored:
+            ref = complex(*stored["auto_last"])
+            check["rel_diff_vs_stored_n1"] = abs(auto2[-1] - ref) / abs(ref)
+            check["matches_stored_n1"] = bool(check["rel_diff_vs_stored_n1"] < 1e-9)
+    except Exception:
+        pass
     line = {"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(config, steps_per_launch=K, kernel=pr.kernel_name(),
+            "dtype": "f64", "data": "synthetic", "config": dict(config, steps_per_launch=K, kernel=roof["whole_step"]["kernels"],
                                                                  trajectories_per_gpu=n_local),
             "e2e": {"value": n_total * K / (ms_e2e * 1e-3), "unit": unit,
                     "h2d_bytes_per_step": int(ens_bytes / K), "d2h_bytes_per_step": 40,
                     "note": "ensemble upload from pinned host memory + state initialisation + K steps + correlation functions to host"},
             "gpu_launches": int(launches), "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC_BYTES_PER_TRAJ_STEP.get(dom_kernel, None) and TRAFFIC_BYTES_PER_TRAJ_STEP[dom_kernel] * n_local * K,
-                         "kernel": dom_kernel, "kernel_ms": dom_ms, "flop_per_trajectory_step": dom_flop, "peak_source": peak_src,
-                         "whole_step": {"achieved": achieved_step, "frac": achieved_step / peak, "ms": ms_kernel,
-                                        "flop_per_trajectory_step": flop, "kernels": pr.kernel_name(),
-                                        "kernel_ms": {"qp_path": float(kt[0]), "rk4": float(kt[1]), "lu": float(kt[2]), "finish": float(kt[3])}},
-                         "note": "FP64 pipe (DMMA/DFMA, measured 37.17 TFLOP/s); achieved = algorithmic flops of the dominant kernel "
-                                 "(16 d^3 per trajectory-step: 4 RK4 stages x H [Mqq|Mqp]) / its device time from CUDA events on the "
-                                 "launching stream; whole_step = (16 + 8/3) d^3 over ALL kernels of the step. Padding (60->64 rows) and "
-                                 "structural zeros are not counted. traffic = DRAM bytes of the dominant kernel from the committed ncu "
-                                 "capture (profiles/), scaled to this launch"},
-            "check": {"C0": [c0.real, c0.imag], "auto_last": [auto[-1].real, auto[-1].imag]}}
-    if not args.no_cpu_baseline:
-        n_s = 1024 if d >= 32 else 8192
+            "roofline": dict(roof, peak_source=peak_src,
+                             note="achieved = algorithmic flops of the dominant kernel (16 d^3 per trajectory-step: 4 RK4 stages x "
+                                  "H [Mqq|Mqp]; + 8 d' d^2 when k_rk4_stream also applies the left prefactor factors) / its device time from "
+                                  "CUDA events on the launching stream; whole_step = all algorithmic flops (SURVEY 8d) over ALL kernels "
+                                  "of the step. Padding (60->64 rows), Hessian formation and structural zeros are not counted. traffic = "
+                                  "DRAM bytes per trajectory-step of the dominant kernel from the committed ncu capture, scaled to this launch"),
+            "check": check}
+    if roofline_dense is not None:
+        line["roofline_dense"] = roofline_dense
+    if not args.no_cpu_baseline and world == 1:
+        n_s = 4096 if d >= 32 else 32768             # 10-30 s of CPU work on the box's host cores
         ns = 10
         v, cores, el = cpu_run(model, G, Q, q0, p0, n_s, ns)
         line["cpu_baseline"] = {"value": v, "unit": unit, "cores": cores, "kind": "port",

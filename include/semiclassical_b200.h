@@ -171,6 +171,9 @@ int sc_engine_get_timing(sc_engine *eng, double *ms4_host);
 /* all SC_TIMING_SLOTS slots: { path (+ overlap terms), RK4/monodromy, LU, finish, right factors (k_rmult), potential
  * Hessians, 0, 0 } of the column pipelines (propagators.py:645-655 has no counterpart: instrumentation only) */
 int sc_engine_get_timing_slots(sc_engine *eng, double *ms_host, int nslots);
+/* FP64 roofline denominator measured on the current device (no reference counterpart): register-resident chains of
+ * mma.sync.m8n8k4.f64 and of DFMA on every SM, best of `reps`, CUDA events.  out_host[0] = DMMA TFLOP/s, [1] = DFMA TFLOP/s */
+int sc_measure_fp64_peak(double *out_host, int reps, void *stream);
 /* run-time options (no reference counterpart; measurement / diagnostics):
  *   "dense_engine" = 1  separable potentials (Morse / AS, NonHarmonic) are propagated by the general dense column pipeline
  *                       (sc_stream.cuh: their diagonal Hessians are expanded to full d x d matrices per stage) instead of

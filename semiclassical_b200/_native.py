@@ -94,6 +94,7 @@ _SIGNATURES = {
     "sc_engine_wavefunction": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, _vp]),
     "sc_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "sc_engine_kernel_name": (ctypes.c_char_p, [_vp]),
+    "sc_measure_fp64_peak": (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     "sc_engine_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
     "sc_engine_set_timing": (ctypes.c_int, [_vp, ctypes.c_int]),
     "sc_engine_get_timing": (ctypes.c_int, [_vp, _vp]),

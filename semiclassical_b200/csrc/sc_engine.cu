@@ -1248,6 +1248,75 @@ extern "C" int sc_engine_wavefunction(sc_engine *e, const double *Gt_host, doubl
   return SC_OK;
 }
 
+// ------------------------------------------------------------------ FP64 roofline denominator, measured live
+// register-resident chains of mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) and of DFMA on every SM; best of `reps` runs with
+// CUDA events.  out_host[0] = DMMA TFLOP/s, out_host[1] = DFMA TFLOP/s (same kernels as tools/fp64_peak.cu)
+namespace {
+template <int ILP>
+__global__ void k_peak_dmma(double *out, int iters, double a, double b) {
+  double c0[ILP], c1[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) { c0[i] = threadIdx.x * 1e-3; c1[i] = i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) dmma884(c0[i], c1[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += c0[i] + c1[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int ILP>
+__global__ void k_peak_dfma(double *out, int iters, double a, double b) {
+  double acc[ILP];
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) acc[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < ILP; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" int sc_measure_fp64_peak(double *out_host, int reps, void *stream) {
+  if (!out_host) return fail(SC_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 148;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int threads = 512, blocks = sms * 2, iters = 20000;
+  double *out = nullptr;
+  CU(cudaMalloc(&out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  double best[2] = {0.0, 0.0};
+  if (reps < 1) reps = 1;
+  for (int which = 0; which < 2; ++which)
+    for (int r = 0; r < reps + 1; ++r) {          // first run: warm-up
+      CU(cudaEventRecord(e0, st));
+      if (which == 0) k_peak_dmma<8><<<blocks, threads, 0, st>>>(out, iters, 1.0000001, 1e-9);
+      else k_peak_dfma<8><<<blocks, threads, 0, st>>>(out, iters, 1.0000001, 1e-9);
+      CU(cudaEventRecord(e1, st));
+      CU(cudaEventSynchronize(e1));
+      float ms = 0.0f;
+      CU(cudaEventElapsedTime(&ms, e0, e1));
+      const double flop = (which == 0 ? 2.0 * 256 * 8 * iters * (double)blocks * (threads / 32)
+                                      : 2.0 * 8 * iters * (double)blocks * threads);
+      if (r > 0) best[which] = std::max(best[which], flop / (ms * 1e-3) / 1e12);
+    }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  out_host[0] = best[0];
+  out_host[1] = best[1];
+  return SC_OK;
+}
+
 // run-time options of an engine (diagnostics / measurement; defaults are the production dispatch)
 extern "C" int sc_engine_set_option(sc_engine *e, const char *name, int value) {
   if (!e || !name) return fail(SC_ERR_INVALID, "null argument");

@@ -234,6 +234,15 @@ class HermanKlukPropagator(object):
         """
         assert Gamma_0.size() == self.Gamma_i.size(), "Width parameter matrix Gamma_0 has wrong dimensions."
         assert _is_symmetric_non_negative(Gamma_0), "Gamma_0 has to be symmetric and positive semi-definite."
+        zi, probi = self.sample_ensemble(q0, p0, Gamma_0, ntraj)
+        self._install(zi, probi, ntraj_total)
+
+    def sample_ensemble(self, q0, p0, Gamma_0, ntraj):
+        """
+        draws ntraj phase-space points from P(qi,pi) ~ |<qi,pi,Gamma_i|q0,p0,Gamma_0>|^2 with torch's CUDA generator
+        (propagators.py:493-555) WITHOUT installing them: returns zi (2 dim, ntraj), probi (ntraj,) on the device.  Ranks that
+        seed the generator identically draw the same global ensemble and install their slice with set_ensemble().
+        """
         self._prepare(q0, p0, Gamma_0)
         d = self.dim
         G0 = Gamma_0.detach().to('cpu', torch.float64)
@@ -258,7 +267,7 @@ class HermanKlukPropagator(object):
         logger.info(f"number of dimensions   :  {d}")
         logger.info(f"zero dimensions        :  {d - nnz}")
         logger.info(f"number of trajectories :  {ntraj}")
-        self._install(zi, probi, ntraj_total)
+        return zi, probi
 
     def set_ensemble(self, q0, p0, Gamma_0, zi, probi, ntraj_total=None):
         """install an externally sampled ensemble: zi (2 dim, n), probi (n,) (ensemble injection)"""
