@@ -33,7 +33,7 @@ def T(x):
 
 
 def _propagate(name, propagators, potential, model_fields, Gi, Gt, G0, q0, p0, ntraj, dt, nt, en0,
-               kind="HK", alpha=None, beta=None, seed=0):
+               kind="HK", alpha=None, beta=None, seed=0, nkeep=NKEEP):
     torch.manual_seed(seed)
     if kind == "WM":
         pr = propagators.WaltonManolopoulosPropagator(T(Gi), T(Gt), alpha, beta)
@@ -46,7 +46,7 @@ def _propagate(name, propagators, potential, model_fields, Gi, Gt, G0, q0, p0, n
     out.update(kind=kind, Gamma_i=Gi, Gamma_t=Gt, Gamma_0=G0, q0=q0, p0=p0, dt=dt, nt=nt, energy0_es=en0,
                zi=zi, probi=probi, autocorrelation=auto, ic_correlation=ic,
                t_final=float(pr.t),
-               y_final=pr.y.numpy()[:, :NKEEP].copy(),
+               y_final=pr.y.numpy()[:, :nkeep].copy(),
                c_final=pr.c.numpy().copy(),
                c2_final=pr.sign_trackers["prefactorC"]["previous"].numpy().copy(),
                signs_C=pr.sign_trackers["prefactorC"]["signs"].numpy().real.copy())
@@ -110,13 +110,14 @@ def methylium_case(name, propagators, potentials, readers, units, ntraj, nt, kin
     _propagate(name, propagators, pot, fields, G0, G0, G0, x0, np.zeros_like(x0), ntraj, dt, nt, en_zpt, kind=kind, **kw)
 
 
-def gdml_potential_case(name, gdml_predictor, model, pos, nbatch, seed, jitter=0.05):
+def gdml_potential_case(name, gdml_predictor, model, pos, nbatch, seed, jitter=0.05, store_model=False):
     rng = np.random.default_rng(seed)
     pred = gdml_predictor.GDMLPredict(model)
     r = pos[None, :] + jitter * rng.standard_normal((nbatch, len(pos)))
     e, g, h = pred.forward(T(r))
     path = os.path.join(GOLDEN, name + ".npz")
-    np.savez_compressed(path, r=r, energy=e.numpy(), grad=g.numpy(), hess=h.numpy())
+    extra = gdml_model_fields(model) if store_model else {}
+    np.savez_compressed(path, r=r, energy=e.numpy(), grad=g.numpy(), hess=h.numpy(), **extra)
     print(f"{name:28s} B={nbatch} E[0]={e[0].item():.8f} |hess|max={h.abs().max().item():.3e} "
           f"{os.path.getsize(path)/1024:.0f} KB")
 
@@ -154,37 +155,66 @@ def fit_small_gdml(n_atoms=4, n_train=24, sig=12, seed=5, k_spring=0.3, jitter=0
     return model, pos.reshape(-1)
 
 
-def gdml_dynamics_case(name, propagators, potentials, gdml_predictor, ntraj, nt):
-    """HK dynamics on a small fitted sGDML surface (N=4 atoms, d=12, Gamma of rank 6 like a real molecule)"""
-    model, pos = fit_small_gdml()
+def coumarin_model(units):
+    """the reference's real sGDML fixture (tests/DATA/GDML: coumarin, 17 atoms, 200 training points, sig 80) and the
+    geometry of coumarin.xyz in bohr; atomic masses from the element symbols"""
+    ddir = os.path.join(refrun.REFERENCE_ROOT, "tests", "DATA", "GDML")
+    model = dict(np.load(os.path.join(ddir, "coumarin_forces_au-wB97XD_def2SVP-train200-sym1.npz"), allow_pickle=True))
+    xyz = np.loadtxt(os.path.join(ddir, "coumarin.xyz"), skiprows=2, usecols=(1, 2, 3)) / units.bohr_to_angs
+    sym = np.loadtxt(os.path.join(ddir, "coumarin.xyz"), skiprows=2, usecols=(0,), dtype=str)
+    amu = {"C": 12.011, "H": 1.008, "O": 15.999}
+    masses = np.repeat(np.array([amu[s] for s in sym]) * units.amu_to_aumass, 3)
+    return model, xyz.reshape(-1), masses
+
+
+def gdml_model_fields(model):
+    """the arrays a test needs to rebuild the model (they travel with the fixture: the reference's npz does not)"""
+    return dict(gdml_sig=int(model['sig']), gdml_c=float(model['c']), gdml_std=float(model['std']),
+                gdml_R_desc=np.asarray(model['R_desc'], dtype=np.float64),
+                gdml_R_d_desc_alpha=np.asarray(model['R_d_desc_alpha'], dtype=np.float64))
+
+
+def gdml_dynamics_case(name, propagators, potentials, gdml_predictor, ntraj, nt, model=None, pos=None, masses=None,
+                       dt_fs=0.05, minimize=True, model_fixture=None, nkeep=NKEEP):
+    """HK dynamics on an sGDML surface: default = small fitted model (N=4 atoms, d=12, Gamma of rank 6 like a real
+    molecule); with model/pos/masses given: the real coumarin fixture (d=51, d'=45)"""
+    if model is None:
+        model, pos = fit_small_gdml()
+        masses = np.repeat(np.array([12.0, 1.0, 14.0, 16.0]) * 1822.888486192, 3)
+    d = len(pos)
 
     class _Nac(object):
         def __init__(self, d, z):
             self._d, self._z = d, z
         def nonadiabatic_coupling(self): return 1.0e-2 * np.cos(np.arange(self._d) + 1.0)
         def atomic_numbers(self): return self._z
-        def masses(self): return np.repeat(np.array([12.0, 1.0, 14.0, 16.0]) * 1822.888486192, 3)
-    d = len(pos)
+        def masses(self): return masses
     nacf = _Nac(d, model['z'])
     pot = potentials.MolecularGDMLPotential(model, nacf)
-    masses = nacf.masses()
     # energy origin at the minimum of the fitted surface (cli.py:293-295)
-    pot.minimize(T(pos))
+    if minimize:
+        pot.minimize(T(pos))
     # widths from the Hessian at the (displaced) start geometry; the wavepacket then moves on the surface
     e, g, h = pot.harmonic_approximation(T(pos).unsqueeze(1))
     hm = h[:, :, 0].numpy() / np.sqrt(np.outer(masses, masses))
     w2, V = np.linalg.eigh(0.5 * (hm + hm.T))
     keep = w2 > 1.0e-7
+    if d > 12:
+        keep = np.zeros(d, dtype=bool)
+        keep[6:] = True                      # eigh sorts ascending: the 6 smallest are translations / rotations
+        assert w2[6] > 1.0e-7, w2[:8]
     L = np.sqrt(masses)[:, None] * V[:, keep] * (w2[keep] ** 0.25)[None, :]
     G0 = L @ L.T
     G0 = 0.5 * (G0 + G0.T)
     en0 = float(0.5 * np.sqrt(w2[keep]).sum())
     print("   gdml4: vib. frequencies (cm-1)", np.sqrt(w2[keep]) * 219474.63, " rank", keep.sum(), "origin", pot._origin)
-    fields = dict(potential="gdml", nac=nacf.nonadiabatic_coupling(), masses=masses, origin=pot._origin,
-                  gdml_sig=model['sig'], gdml_c=model['c'], gdml_std=model['std'],
-                  gdml_R_desc=model['R_desc'], gdml_R_d_desc_alpha=model['R_d_desc_alpha'])
-    dt = 0.05 / 0.02418884326505
-    _propagate(name, propagators, pot, fields, G0, G0, G0, pos, np.zeros(d), ntraj, dt, nt, en0)
+    fields = dict(potential="gdml", nac=nacf.nonadiabatic_coupling(), masses=masses, origin=pot._origin)
+    if model_fixture is None:
+        fields.update(gdml_model_fields(model))
+    else:
+        fields.update(gdml_model_fixture=model_fixture)      # the model arrays live in that fixture
+    dt = dt_fs / 0.02418884326505
+    _propagate(name, propagators, pot, fields, G0, G0, G0, pos, np.zeros(d), ntraj, dt, nt, en0, nkeep=nkeep)
 
 
 def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, dt, nt, en0, nx, seed=0, xspread=0.3):
@@ -271,12 +301,10 @@ def main():
         model, pos = workloads.gdml_synthetic(n_atoms=5, n_train=16, sig=10, seed=3)
         gdml_potential_case("gdml_pot_n5", gdml_predictor, model, pos, 16, seed=2)
     if want("gdml_pot_coumarin"):
-        ddir = os.path.join(refrun.REFERENCE_ROOT, "tests", "DATA", "GDML")
-        model = dict(np.load(os.path.join(ddir, "coumarin_forces_au-wB97XD_def2SVP-train200-sym1.npz"), allow_pickle=True))
-        xyz = np.loadtxt(os.path.join(ddir, "coumarin.xyz"), skiprows=2, usecols=(1, 2, 3)) / units.bohr_to_angs
-        # the fitted model itself is 500 KB: store only a hash-free recipe (shapes + outputs); the test rebuilds
-        # nothing from it, it is a known-answer check for the oracle run inside this container only
-        gdml_potential_case("gdml_pot_coumarin", gdml_predictor, model, xyz.reshape(-1), 2, seed=4, jitter=0.02)
+        # the reference's real fixture; the fitted model's arrays are stored with the outputs so that the tests can rebuild
+        # the potential on the GPU box (the reference's npz does not travel)
+        model, xyz, _ = coumarin_model(units)
+        gdml_potential_case("gdml_pot_coumarin", gdml_predictor, model, xyz, 4, seed=4, jitter=0.02, store_model=True)
     if want("diag_as5"):
         diag_morse("diag_as5", propagators, potentials, workloads.as_5modes(0.02), 300, 30, 40)
     if want("diag_as5_rot"):
@@ -291,6 +319,11 @@ def main():
         Gi = np.array([[5.0]])
         diag_case("diag_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 500,
                   float(times[1] - times[0]), nt, 0.5, 128, seed=4, xspread=3.0)
+    if want("hk_gdml_coumarin"):
+        # C5 at fixture size: HK dynamics on the real coumarin sGDML surface, d = 51, d' = 45, 24 steps
+        model, xyz, masses = coumarin_model(units)
+        gdml_dynamics_case("hk_gdml_coumarin", propagators, potentials, gdml_predictor, 40, 24, model=model, pos=xyz,
+                           masses=masses, dt_fs=0.05, model_fixture="gdml_pot_coumarin", nkeep=3)
     if want("hk_gdml4"):
         gdml_dynamics_case("hk_gdml4", propagators, potentials, gdml_predictor, 200, 40)
 

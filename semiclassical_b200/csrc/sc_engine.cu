@@ -749,7 +749,8 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   const size_t tsz = dense ? (size_t)L.mtr * L.nt * 128 : 0;            // doubles of fragment scratch per matrix
   const size_t cmsz = (size_t)dr * dr * 2;                               // doubles per prefactor matrix
   const int dp = (d + 1) & ~1;
-  const size_t per_traj = (size_t)KC * sizeof(double) * (cmsz + 2 + 8 + 2 * d + tsz + (hconst ? 0 : 4 * hsz + 4 * dp));
+  const size_t per_traj = (size_t)KC * sizeof(double) * (cmsz + 2 + 8 + 2 * d + tsz + (hconst ? 0 : 4 * hsz + 4 * dp)) +
+                          sizeof(double) * (8 * d + 4);                       // + path state of the sGDML stage kernels
   size_t budget = (size_t)6 << 30;
   if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
   long long ntb = (long long)(budget / per_traj);
@@ -764,7 +765,8 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   double *qp = base;                                          base += (size_t)KC * ntb * 2 * d;
   double *T = dense ? base : nullptr;                         base += (size_t)KC * ntb * tsz;
   double *hs = hconst ? e->stream_const : base;                 base += hconst ? 0 : (size_t)KC * ntb * 4 * hsz;
-  double *hd = base;                                            // stage diagonals of the potentials whose Hessian is expanded
+  double *hd = base;                                            base += hconst ? 0 : (size_t)KC * ntb * 4 * dp;
+  double *pst = base;                                           // sGDML: path state, stage positions, V, grad
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
@@ -791,6 +793,20 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
         const size_t psm = sizeof(double) * ((size_t)d * (d | 1) + PATH_WARPS * 2 * ((d + 1) & ~1));
         CU(cudaFuncSetAttribute(k_path_rotated, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         k_path_rotated<<<(nt + PATH_WARPS - 1) / PATH_WARPS, 32 * PATH_WARPS, psm, st>>>(e->dev, P, h, ks, (int)t0, nt, qp, aux, hd);
+      } else if (P.type == POT_GDML) {
+        // sGDML: E, grad, Hessian of every stage by k_gdml_eval; the Hessian lands in the stream image of its stage
+        double *rbuf = pst + (size_t)6 * d * nt + 2 * nt, *Vb = rbuf + (size_t)d * nt, *gb = Vb + nt;
+        const int blk = (nt + 127) / 128;
+        k_gstage_begin<<<blk, 128, 0, st>>>(e->dev, (int)t0, nt, pst, rbuf);
+        CU(cudaGetLastError());
+        for (int step = 0; step < ks; ++step)
+          for (int sg = 1; sg <= 4; ++sg) {
+            if (launch_gdml_eval(P, nt, rbuf, Vb, gb, hs + ((size_t)(step * 4 + sg - 1) * nt) * hsz, st, L.ldh, hsz))
+              return fail(SC_ERR_UNSUPPORTED, "sGDML model outside the kernel's envelope");
+            k_gstage_adv<<<blk, 128, 0, st>>>(e->dev, P, h, sg, step, step + 1 == ks ? 1 : 0, (int)t0, nt, pst, Vb, gb, rbuf, qp, aux);
+            CU(cudaGetLastError());
+            e->launches += 2;
+          }
       } else if ((P.type == POT_MORSE || P.type == POT_NONHARMONIC) && e->dev.diag) {
         k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);      // overlap terms included
         aux_done = true;
@@ -804,7 +820,7 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
         k_aux_terms<<<grid, 256, 0, st>>>(e->dev, ks, (int)t0, nt, qp, aux);
         CU(cudaGetLastError());
       }
-      if (!hconst) {
+      if (!hconst && P.type != POT_GDML) {
         timing_mark(e, TS_POT, st);
         CU(launch_expand(P, P.type == POT_ROTATED_MORSE ? 1 : 0, ks, nt, hd, hs, sm, st));
         e->launches += 1;
@@ -1053,7 +1069,8 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
   if (nsteps < 1) return SC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = set_nac(e, pot->n1.data(), st)) return rc;
-  if (pot->dev.type == POT_GDML) return fail(SC_ERR_UNSUPPORTED, "sGDML potentials run through the stage interface");
+  if (pot->dev.type == POT_GDML && !stream_supported(e->dev, pot->dev, false))
+    return fail(SC_ERR_UNSUPPORTED, "sGDML potentials with d < 17 or d > 64 run through the stage interface");
   if (!corr_dev) {
     if (int rc = ensure_corr(e, nsteps, st)) return rc;
     corr_dev = e->corr_dev;

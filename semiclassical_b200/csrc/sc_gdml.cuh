@@ -81,7 +81,9 @@ __device__ __forceinline__ int pair_index(int i, int j) { return i * (i - 1) / 2
 
 __global__ void __launch_bounds__(GDML_THREADS)
 k_gdml_eval(PotDev P, int n, const double *__restrict__ r, double *__restrict__ V, double *__restrict__ grad,
-            double *__restrict__ hess, GdmlLayout L, int use_bulk) {
+            double *__restrict__ hess, GdmlLayout L, int use_bulk, int hs_ld, size_t hs_stride) {
+  // hs_ld > 0: the Hessian of geometry g goes to hess + g hs_stride as a row-major image with leading dimension hs_ld
+  // (zero padding columns): the stream image k_rk4_stream consumes (sc_stream.cuh); else batch-last (X, X, n)
   extern __shared__ __align__(16) double gsm[];
   __shared__ __align__(8) uint64_t bars[2];
   const int N = P.n_atoms, M = P.n_train, D = P.n_desc, X = 3 * N, Xp = L.Xp;
@@ -276,16 +278,28 @@ k_gdml_eval(PotDev P, int n, const double *__restrict__ r, double *__restrict__ 
           // diagonal blocks hold G + G^T already symmetrised element-wise: (u,v) and (v,u) are both computed
           const double val = hacc[u][v] * P.gstd;
           const int x = 3 * bI + u, y = 3 * bJ + v;
-          hess[((size_t)x * X + y) * n + geom] = val;
-          if (bI != bJ) hess[((size_t)y * X + x) * n + geom] = val;
+          if (hs_ld > 0) {
+            double *Hg = hess + (size_t)geom * hs_stride;
+            Hg[x * hs_ld + y] = val;
+            if (bI != bJ) Hg[y * hs_ld + x] = val;
+          } else {
+            hess[((size_t)x * X + y) * n + geom] = val;
+            if (bI != bJ) hess[((size_t)y * X + x) * n + geom] = val;
+          }
         }
+    }
+    if (hess && hs_ld > X) {
+      double *Hg = hess + (size_t)geom * hs_stride;
+      const int np = hs_ld - X;
+      for (int i = t; i < X * np; i += GDML_THREADS) Hg[(i / np) * hs_ld + X + i % np] = 0.0;
     }
     __syncthreads();
   }
 }
 
 // returns 0 on launch, 1 if the configuration is outside the kernel's envelope
-static int launch_gdml_eval(const PotDev &P, int n, const double *r, double *V, double *grad, double *hess, cudaStream_t st) {
+static int launch_gdml_eval(const PotDev &P, int n, const double *r, double *V, double *grad, double *hess, cudaStream_t st,
+                            int hs_ld = 0, size_t hs_stride = 0) {
   const int N = P.n_atoms, D = P.n_desc;
   if (N * (N + 1) / 2 > GDML_THREADS) return 1;
   const GdmlLayout L = make_gdml_layout(N, D);
@@ -301,7 +315,7 @@ static int launch_gdml_eval(const PotDev &P, int n, const double *r, double *V, 
   int grid = sms * per_sm;
   if (grid > n) grid = n;
   const int use_bulk = ((D * sizeof(double)) % 16 == 0) ? 1 : 0;
-  k_gdml_eval<<<grid, GDML_THREADS, smem, st>>>(P, n, r, V, grad, hess, L, use_bulk);
+  k_gdml_eval<<<grid, GDML_THREADS, smem, st>>>(P, n, r, V, grad, hess, L, use_bulk, hs_ld, hs_stride);
   return 0;
 }
 

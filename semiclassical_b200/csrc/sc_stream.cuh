@@ -655,6 +655,75 @@ k_path_rotated(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, dou
   if (lane == 0) rec[2 * d] = S;
 }
 
+// (q, p, S) path of potentials evaluated by their own batched kernel (sGDML, sc_gdml.cuh): one thread per trajectory, state
+// in batch-last arrays (coalesced over the trajectories) of the path scratch pst = [qa | pa | qs | ps | accq | accp] (each d x nt)
+// + [S | accS] (nt).  k_gstage_begin loads the records and emits the stage-1 positions; k_gstage_adv consumes V, grad of stage s
+// (classical RK4, propagators.py:114-119, 361-368) and emits the next positions, after stage 4 the per-step outputs.
+__global__ void k_gstage_begin(EngDev E, int traj0, int nt, double *__restrict__ pst, double *__restrict__ r_out) {
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= nt) return;
+  const int d = E.d;
+  const double *rec = E.rec + (size_t)(traj0 + tl) * E.rs;
+  const size_t dn = (size_t)d * nt;
+  for (int a = 0; a < d; ++a) {
+    const double q = rec[a], p = rec[d + a];
+    const size_t i = (size_t)a * nt + tl;
+    pst[i] = q; pst[dn + i] = p; pst[2 * dn + i] = q; pst[3 * dn + i] = p; pst[4 * dn + i] = 0.0; pst[5 * dn + i] = 0.0;
+    r_out[i] = q;
+  }
+  pst[6 * dn + tl] = rec[2 * d];
+  pst[6 * dn + nt + tl] = 0.0;
+}
+
+__global__ void k_gstage_adv(EngDev E, PotDev P, double h, int s, int step, int last_step, int traj0, int nt, double *__restrict__ pst,
+                             const double *__restrict__ V, const double *__restrict__ grad, double *__restrict__ r_out,
+                             double *__restrict__ qp, double *__restrict__ aux) {
+  const int tl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tl >= nt) return;
+  const int d = E.d;
+  const size_t dn = (size_t)d * nt;
+  const double cnext = (s == 3) ? h : 0.5 * h;
+  const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
+  double tk = 0.0;
+  double *qo = qp + ((size_t)step * nt + tl) * 2 * d;
+  double *rec = E.rec + (size_t)(traj0 + tl) * E.rs;
+  for (int a = 0; a < d; ++a) {
+    const size_t i = (size_t)a * nt + tl;
+    const double im = P.imass[a], ps = pst[3 * dn + i];
+    const double kq = ps * im, kp = -grad[i];
+    tk += 0.5 * ps * ps * im;
+    const double aq = pst[4 * dn + i] + wgt * kq, ap = pst[5 * dn + i] + wgt * kp;
+    if (s < 4) {
+      pst[4 * dn + i] = aq;
+      pst[5 * dn + i] = ap;
+      const double qs = pst[i] + cnext * kq;
+      pst[2 * dn + i] = qs;
+      pst[3 * dn + i] = pst[dn + i] + cnext * kp;
+      r_out[i] = qs;
+    } else {
+      const double q = pst[i] + h / 6.0 * aq, p = pst[dn + i] + h / 6.0 * ap;
+      pst[i] = q; pst[dn + i] = p; pst[2 * dn + i] = q; pst[3 * dn + i] = p; pst[4 * dn + i] = 0.0; pst[5 * dn + i] = 0.0;
+      r_out[i] = q;
+      qo[a] = q;
+      qo[d + a] = p;
+      if (last_step) { rec[a] = q; rec[d + a] = p; }
+    }
+  }
+  const double v = V[tl];
+  const double aS = pst[6 * dn + nt + tl] + wgt * (tk - v);
+  if (s < 4) {
+    pst[6 * dn + nt + tl] = aS;
+  } else {
+    const double S = pst[6 * dn + tl] + h / 6.0 * aS;
+    pst[6 * dn + tl] = S;
+    pst[6 * dn + nt + tl] = 0.0;
+    double *ax = aux + ((size_t)step * nt + tl) * 8;
+    ax[6] = S;
+    ax[7] = tk + v;
+    if (last_step) rec[2 * d] = S;
+  }
+}
+
 // Hessian stream images (d x LDH, zero padded) from the stage diagonals hd (item, dp), item = (step, tl, stage):
 //   ROT = 0  H = diag(h)                    (separable models run through the general dense engine)
 //   ROT = 1  H = Q diag(h) Q^T              (rotated Morse fixture) on the tensor pipe: A fragment = Q[i][k] h[k], B fragment =
@@ -877,7 +946,7 @@ k_corr_now(EngDev E, double *__restrict__ partials) {
 // whatever it is given; sc_chunk.cuh is the path that knows about the structure)
 static bool stream_supported(const EngDev &E, const PotDev &P, bool dense_engine) {
   if (E.d < 17 || E.d > 64) return false;
-  if (P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE) return true;
+  if (P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE || P.type == POT_GDML) return true;
   return dense_engine && E.diag && E.dr == E.d && (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
 }
 

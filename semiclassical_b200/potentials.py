@@ -245,7 +245,12 @@ class MolecularHarmonicPotential(_MolecularPotentialBase):
 
 class MolecularGDMLPotential(_MolecularPotentialBase):
     """sGDML ground-state surface with analytic Hessians (potentials.py:641-744, gdml_predictor.py:35-250)"""
-    _fused_step = False
+
+    @property
+    def _fused_step(self):
+        # 17 <= dim <= 64: the dense column pipeline drives k_gdml_eval itself (Hessians written straight into the stream
+        # image of their RK4 stage); smaller / larger molecules go through the stage interface
+        return 17 <= self._dim <= 64
 
     def __init__(self, model_pot, nac_fchk):
         model = dict(model_pot)

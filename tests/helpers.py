@@ -28,6 +28,10 @@ def potential_from_golden(g):
         return potentials.MolecularHarmonicPotential.from_arrays(g['pos0'], g['energy0'], g['grad0'], g['hess0'],
                                                                  g['masses'], g['nac'], float(g['origin']))
     if kind == "gdml":
+        if 'gdml_model_fixture' in g.files:              # the model arrays live in another fixture
+            gm = load_golden(str(g['gdml_model_fixture']))
+            g = dict(g.items())
+            g.update({k: gm[k] for k in gm.files if k.startswith('gdml_')})
         D = g['gdml_R_desc'].shape[0]
         n_atoms = len(g['masses']) // 3
         model = dict(sig=int(g['gdml_sig']), c=float(g['gdml_c']), std=float(g['gdml_std']), R_desc=g['gdml_R_desc'],

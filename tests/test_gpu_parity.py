@@ -191,6 +191,55 @@ def test_gdml_kernel_matches_reference(name, kwargs, cuda_device):
     assert np.abs(hess - hess.transpose(1, 0, 2)).max() < 1.0e-13 * np.abs(hess).max()
 
 
+def _coumarin_model(g):
+    d = g['r'].shape[1]
+    return dict(sig=int(g['gdml_sig']), c=float(g['gdml_c']), std=float(g['gdml_std']), R_desc=g['gdml_R_desc'],
+                R_d_desc_alpha=g['gdml_R_d_desc_alpha'], perms=np.arange(d // 3)[None, :],
+                tril_perms_lin=np.arange(g['gdml_R_desc'].shape[0])), d
+
+
+def test_gdml_kernel_on_the_real_coumarin_fixture(cuda_device):
+    """k_gdml_eval on the reference's real fitted model (coumarin, 17 atoms, 200 training points, sig 80) vs the
+    reference's own GDMLPredict.forward outputs (potential-level parity on the real fixture)"""
+    from semiclassical_b200 import potentials
+    g = helpers.load_golden("gdml_pot_coumarin")
+    model, d = _coumarin_model(g)
+    pot = potentials.MolecularGDMLPotential.from_arrays(model, np.ones(d), np.zeros(d))
+    V, grad, hess = pot.harmonic_approximation(T(g['r'].T.copy()).to(cuda_device))
+    V, grad, hess = V.cpu().numpy(), grad.cpu().numpy(), hess.cpu().numpy()
+    # fitted alphas ~7e11: 12 digits cancel in the kernel sum; the reference's own outputs move by 2.3e-9 / 3.8e-9 / 3.2e-9
+    # absolute (E / grad / Hessian) under a permutation of its training set -- the bar is a few times that
+    assert np.abs(V - g['energy']).max() < 2.0e-8
+    assert np.abs(grad.T - g['grad']).max() < 2.0e-8 and relerr(grad.T, g['grad']) < 5.0e-7
+    assert np.abs(hess.transpose(2, 0, 1) - g['hess']).max() < 2.0e-8 and relerr(hess.transpose(2, 0, 1), g['hess']) < 5.0e-8
+    assert np.abs(hess - hess.transpose(1, 0, 2)).max() < 1.0e-13 * np.abs(hess).max()
+
+
+def test_hk_on_the_real_coumarin_sgdml_surface(cuda_device):
+    """C5 at fixture size: HK dynamics (d = 51, d' = 45, 40 trajectories, 24 steps) on the real coumarin sGDML surface vs the
+    reference's golden -- fused launches on the dense column pipeline (k_gdml_eval writes the Hessian of every RK4 stage
+    straight into the stream image k_rk4_stream consumes) and, second, step by step through the drop-in API.
+    Tolerance 1e-7: the kernel sum over the training set is cancellation-prone (the reference's own gradient moves by
+    ~4e-9 under a permutation of the training points) and 24 steps of dynamics amplify it."""
+    g = helpers.load_golden("hk_gdml_coumarin")
+    pot = helpers.potential_from_golden(g)
+    nt, e0, dt = int(g['nt']), float(g['energy0_es']), float(g['dt'])
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    a0, i0 = pr.autocorrelation(e0), pr.ic_correlation(pot, e0)
+    a, i = pr.propagate(pot, dt, nt - 1, e0)
+    assert pr.kernel_name().startswith("k_rk4_stream+k_rmult+")
+    assert relerr(np.concatenate(([a0], a)), g['autocorrelation']) < 1.0e-7
+    assert relerr(np.concatenate(([i0], i)), g['ic_correlation']) < 1.0e-7
+    pr.step(pot, dt)
+    nk = g['y_final'].shape[1]
+    assert relerr(pr.y[:, :nk].cpu().numpy(), g['y_final']) < 1.0e-7
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
+    pr2 = helpers.propagator_from_golden(g, cuda_device)
+    auto, ic = run_loop(pr2, pot, dt, nt, e0)
+    assert relerr(auto, g['autocorrelation']) < 1.0e-7
+    assert relerr(ic, g['ic_correlation']) < 1.0e-7
+
+
 def test_gdml_kernel_large_batch_against_oracle(cuda_device):
     """1000 geometries (several per CTA, every tile phase exercised) vs the C oracle"""
     from oracle import oracle
