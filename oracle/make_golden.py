@@ -110,6 +110,43 @@ def methylium_case(name, propagators, potentials, readers, units, ntraj, nt, kin
     _propagate(name, propagators, pot, fields, G0, G0, G0, x0, np.zeros_like(x0), ntraj, dt, nt, en_zpt, kind=kind, **kw)
 
 
+def c2_full_size_case(name, propagators, potentials, ntraj=10000, seed=2002):
+    """BASELINE configs[1] at its full size: AS 5 modes (chi = 0.02), Walton-Manolopoulos alpha = beta = 500, 10^4 trajectories,
+    time grid of tests/test_propagators.py:378-382.  The ensemble is NOT stored: it is drawn by oracle.sample_ensemble from a
+    numpy PCG64 stream (seed in the fixture, checksum stored) and injected into the reference propagator (SURVEY 8c recipe);
+    the fixture holds the reference's correlation functions, the three branch-sign vectors and the final determinants."""
+    import oracle as oracle   # this script runs from inside oracle/: the sibling module
+    m = workloads.as_5modes(0.02)
+    G = np.diag(m.omega)
+    dt, nt = workloads.test_time_grid()
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, ntraj, np.random.default_rng(seed))
+    pot = potentials.MorsePotential(T(m.omega.copy()), T(m.chi.copy()), T(m.nac.copy()))
+    torch.manual_seed(0)
+    pr = propagators.WaltonManolopoulosPropagator(T(G), T(G), 500, 500)
+    pr.initial_conditions(T(m.q0), T(m.p0), T(G), ntraj=ntraj)
+    d = len(m.q0)
+    pr.zi = T(zi)
+    pr.probi = T(probi)
+    pr.y[:2 * d, :] = T(zi)
+    del pr.sign_trackers
+    pr._prefactor()
+    auto, ic = refrun.run_reference(pr, pot, dt, nt, m.en_zpt)
+    st = pr.sign_trackers
+    out = dict(potential="morse", omega=m.omega, chi=m.chi, nac=m.nac, kind="WM", alpha=500.0, beta=500.0, Gamma_i=G, Gamma_t=G,
+               Gamma_0=G, q0=m.q0, p0=m.p0, dt=dt, nt=nt, energy0_es=m.en_zpt, ensemble_seed=seed, ntraj=ntraj,
+               zi_checksum=np.array([zi.sum(), np.abs(zi).sum(), zi[0, 0], zi[-1, -1]]), probi_sum=probi.sum(),
+               autocorrelation=auto, ic_correlation=ic, t_final=float(pr.t),
+               signs_C=st["prefactorC"]["signs"].numpy().real.astype(np.int8),
+               signs_detA=st["detA"]["signs"].numpy().real.astype(np.int8),
+               signs_detM=st["detM"]["signs"].numpy().real.astype(np.int8),
+               c_final_sum=np.array([pr.c.numpy().sum()]), detA_final_sum=np.array([pr.detA.numpy().sum()]),
+               detM_final_sum=np.array([pr.detM.numpy().sum()]))
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name:28s} n={ntraj:5d} nt={nt:4d} C(0)={auto[0]:.6f} flips C/A/M = {(out['signs_C'] < 0).sum()}/"
+          f"{(out['signs_detA'] < 0).sum()}/{(out['signs_detM'] < 0).sum()}  {os.path.getsize(path)/1024:.0f} KB")
+
+
 def gdml_potential_case(name, gdml_predictor, model, pos, nbatch, seed, jitter=0.05, store_model=False):
     rng = np.random.default_rng(seed)
     pred = gdml_predictor.GDMLPredict(model)
@@ -319,6 +356,8 @@ def main():
         Gi = np.array([[5.0]])
         diag_case("diag_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 500,
                   float(times[1] - times[0]), nt, 0.5, 128, seed=4, xspread=3.0)
+    if want("c2_wm_as5_n10000"):
+        c2_full_size_case("c2_wm_as5_n10000", propagators, potentials)
     if want("hk_gdml_coumarin"):
         # C5 at fixture size: HK dynamics on the real coumarin sGDML surface, d = 51, d' = 45, 24 steps
         model, xyz, masses = coumarin_model(units)

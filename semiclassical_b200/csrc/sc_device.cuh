@@ -49,6 +49,10 @@ struct EngDev {
   const double2 *wvi;                       // (n) <qi,pi|phi0> / (probi (2 pi)^d)
   double2 *c2, *c;                          // (n) det and principal sqrt
   double *sign;                             // (n) branch sign of sqrt(det)
+  // optional per-step snapshots (K-step fused Walton-Manolopoulos launches): record, sqrt(det), sign of (step, traj)
+  double *snap;                             // (K, n, rs) or null
+  double2 *snap_c;                          // (K, n)
+  double *snap_sign;                        // (K, n)
 };
 
 // ------------------------------------------------------------------ complex helpers ---------

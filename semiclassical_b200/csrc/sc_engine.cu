@@ -81,6 +81,9 @@ struct WMState {
   double *n1_dev = nullptr, *scratch5 = nullptr, *partials = nullptr;
   int tpt = 32, groups = 1, grid = 1;
   size_t smem = 0;
+  // K-step fused launches: snapshots of (step, trajectory) records, per-group rows, HK rows (energies)
+  void *snap = nullptr;
+  size_t snap_cap = 0;
 };
 
 struct sc_potential {
@@ -127,6 +130,7 @@ struct sc_engine {
     if (corr_dev) cudaFree(corr_dev);
     if (chunk_scratch) cudaFree(chunk_scratch);
     if (stream_const) cudaFree(stream_const);
+    if (wm.snap) cudaFree(wm.snap);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
 };
@@ -1076,8 +1080,61 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
     corr_dev = e->corr_dev;
   }
   if (!e->cfg.wm) return run_hk_kernel(e, pot->dev, dt, nsteps, MODE_STEP, corr_dev, st);
-  // Walton-Manolopoulos: the HK kernel advances the trajectories one step at a time, the WM kernel evaluates
-  // the Filinov-smoothed prefactor pieces and the WM contributions of every new time
+  if (e->dev.d <= 16 && !getenv("SC_WM_UNFUSED")) {
+    // Walton-Manolopoulos, K steps per launch: k_hk_generic advances the trajectories KC steps and snapshots every new time
+    // (record, sqrt(det), sign); ONE k_wm_fused launch evaluates the Filinov-smoothed prefactor pieces and the contributions
+    // of all KC times (branch trackers walked in time order per trajectory)
+    WMState &w = e->wm;
+    const int n = e->dev.n;
+    const size_t per_step = sizeof(double) * ((size_t)n * e->dev.rs + 3 * (size_t)n);
+    int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)nsteps, ((size_t)4 << 30) / per_step));
+    if (const char *s = getenv("SC_CHUNK_K")) KC = std::max(1, std::min(KC, atoi(s)));
+    const size_t ngr = (size_t)w.grid * w.groups;
+    const size_t need = per_step * KC + sizeof(double) * (ngr * KC * 4 + (size_t)KC * 5) + 256;
+    if (need > w.snap_cap) {
+      CU(cudaStreamSynchronize(st));
+      if (w.snap) cudaFree(w.snap);
+      w.snap = nullptr;
+      w.snap_cap = 0;
+      CU(cudaMalloc(&w.snap, need));
+      w.snap_cap = need;
+    }
+    double *sb = reinterpret_cast<double *>(w.snap);
+    double *snap = sb;                                              sb += (size_t)KC * n * e->dev.rs;
+    double2 *snap_c = reinterpret_cast<double2 *>(sb);              sb += (size_t)KC * n * 2;
+    double *snap_sign = sb;                                         sb += (size_t)KC * n;
+    double *wpart = sb;                                             sb += ngr * KC * 4;
+    double *hkrows = sb;
+    const int threads = w.tpt * w.groups;
+    for (int s0 = 0; s0 < nsteps; s0 += KC) {
+      const int ks = std::min(KC, nsteps - s0);
+      e->dev.snap = snap;
+      e->dev.snap_c = snap_c;
+      e->dev.snap_sign = snap_sign;
+      int rc = run_hk_kernel(e, pot->dev, dt, ks, MODE_STEP, hkrows, st);
+      EngDev Dsnap = e->dev;
+      e->dev.snap = nullptr;
+      e->dev.snap_c = nullptr;
+      e->dev.snap_sign = nullptr;
+      if (rc) return rc;
+      CU(cudaMemsetAsync(wpart, 0, sizeof(double) * ngr * ks * 4, st));
+      if (w.tpt == 32) {
+        CU(cudaFuncSetAttribute(k_wm_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+        k_wm_fused<32><<<w.grid, threads, w.smem, st>>>(Dsnap, w.dev, w.L, ks, wpart);
+      } else {
+        CU(cudaFuncSetAttribute(k_wm_fused<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+        k_wm_fused<128><<<w.grid, threads, w.smem, st>>>(Dsnap, w.dev, w.L, ks, wpart);
+      }
+      CU(cudaGetLastError());
+      k_wm_reduce_k<<<ks, 160, 0, st>>>(wpart, (int)ngr, ks, 1.0 / (double)e->ntraj_norm, hkrows, corr_dev + 5 * s0);
+      CU(cudaGetLastError());
+      e->launches += 3;
+    }
+    e->kernel_name = "k_hk_generic+k_wm_fused";
+    return SC_OK;
+  }
+  // larger d: the HK pipeline advances the trajectories one step at a time, the WM kernel evaluates the Filinov-smoothed
+  // prefactor pieces and the WM contributions of every new time
   for (int k = 0; k < nsteps; ++k) {
     if (int rc = run_hk_kernel(e, pot->dev, dt, 1, MODE_STEP, e->wm.scratch5, st)) return rc;
     if (int rc = wm_launch(e->wm, e->dev, WM_STEP, 1.0 / (double)e->ntraj_norm, corr_dev + 5 * k, e->wm.scratch5, st)) return rc;

@@ -209,6 +209,22 @@ k_hk_generic(EngDev E, PotDev P, double h, int nsteps, int mode, double *partial
           row[0] += ca.x; row[1] += ca.y; row[2] += ki.x; row[3] += ki.y; row[4] += v8[7];
         }
       }
+      if (E.snap != nullptr && mode == MODE_STEP) {
+        // snapshot of the new time for the fused Walton-Manolopoulos launch (sc_wm.cuh: k_wm_fused)
+        const size_t item = (size_t)step * E.n + traj;
+        double *sr = E.snap + item * E.rs;
+        if (t < d) { sr[t] = q[t]; sr[d + t] = p[t]; }
+        for (int idx = t; idx < NE; idx += TPT) {
+          const int a = idx / W, b = idx % W;
+          sr[E.qps + idx] = Ub[a * ldu + b];
+          sr[E.qps + NE + idx] = Vb[a * ldu + b];
+        }
+        if (t == 0) {
+          sr[2 * d] = S;
+          E.snap_c[item] = cc;
+          E.snap_sign[item] = sign;
+        }
+      }
       Group<TPT>::sync(gid);
     }
     // ---- write back

@@ -560,6 +560,45 @@ __global__ void __launch_bounds__(128) k_wm(EngDev E, WMDev W, WMLayout L, int m
   }
 }
 
+// K time steps per launch: the HK kernel stored the record, sqrt(det) and sign of every (step, trajectory); a group walks the
+// steps of its trajectory IN TIME ORDER (the detA / detM branch trackers are sequential) and adds the contributions of step k
+// to its own row k of partials (ngroups, K, 4) -- zeroed by the host, one writer per row
+template <int TPT>
+__global__ void __launch_bounds__(128) k_wm_fused(EngDev E, WMDev W, WMLayout L, int nsteps, double *partials) {
+  extern __shared__ __align__(16) double2 wm_smem[];
+  const int G = blockDim.x / TPT, gid = threadIdx.x / TPT, t = threadIdx.x % TPT;
+  const int gg = blockIdx.x * G + gid, NG = gridDim.x * G;
+  double2 *ws = wm_smem + (size_t)gid * L.total;
+  for (int traj = gg; traj < E.n; traj += NG) {
+    for (int step = 0; step < nsteps; ++step) {
+      EngDev Es = E;
+      Es.rec = E.snap + (size_t)step * E.n * E.rs;
+      Es.c = E.snap_c + (size_t)step * E.n;
+      Es.sign = E.snap_sign + (size_t)step * E.n;
+      double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+      wm_trajectory<TPT>(Es, W, L, ws, traj, WM_STEP, t, gid, acc4);
+      if (t == 0) {
+        double *row = partials + ((size_t)gg * nsteps + step) * 4;
+        row[0] += acc4[0]; row[1] += acc4[1]; row[2] += acc4[2]; row[3] += acc4[3];
+      }
+    }
+  }
+}
+
+// out (K, 5): columns 0..3 = inv_norm * sum over groups of partials (ngroups, K, 4); column 4 = energy_rows[k][4]
+__global__ void k_wm_reduce_k(const double *partials, int ngroups, int nsteps, double inv_norm, const double *energy_rows, double *out) {
+  const int k = blockIdx.x, j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (j < 4) {
+    double s = 0.0;
+    for (int g = lane; g < ngroups; g += 32) s += partials[((size_t)g * nsteps + k) * 4 + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[k * 5 + j] = s * inv_norm;
+  } else if (j == 4 && lane == 0) {
+    out[k * 5 + 4] = energy_rows[k * 5 + 4];
+  }
+}
+
 // deterministic second pass: out[0..3] = inv_norm * sum over groups; out[4] = energy passthrough
 __global__ void k_wm_reduce(const double *partials, int ngroups, double inv_norm, const double *energy_src, double *out) {
   const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -59,3 +59,13 @@ def propagator_from_golden(g, device, nslice=None):
 def relerr(a, b):
     """max_t |a - b| / max_t |b|  (the parity metric of SURVEY.md section 7.2-4)"""
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / np.abs(np.asarray(b)).max())
+
+
+def regenerate_ensemble(g):
+    """ensemble of a fixture that stores only its numpy seed (oracle.sample_ensemble stream) and a checksum"""
+    from oracle import oracle
+    zi, probi = oracle.sample_ensemble(g['Gamma_i'], g['Gamma_0'], g['q0'], g['p0'], int(g['ntraj']),
+                                       np.random.default_rng(int(g['ensemble_seed'])))
+    chk = np.array([zi.sum(), np.abs(zi).sum(), zi[0, 0], zi[-1, -1]])
+    assert np.allclose(chk, g['zi_checksum'], rtol=1e-13, atol=0.0), "numpy's PCG64 normal stream changed: regenerate the fixture"
+    return zi, probi

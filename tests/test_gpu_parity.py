@@ -168,6 +168,31 @@ def test_wm_fused_propagate_matches_reference(name, cuda_device):
     _check_wm_signs(pr, g)
 
 
+def test_c2_full_size_wm_fused_launches(cuda_device):
+    """BASELINE configs[1] at its FULL size: AS 5 modes, WM alpha = beta = 500, 10^4 trajectories, 100 steps, against the
+    reference's golden (ensemble regenerated from its numpy seed).  K-step fused launches (k_hk_generic snapshots +
+    ONE k_wm_fused per 33 steps); all three branch-sign vectors identical"""
+    from semiclassical_b200 import propagators
+    g = helpers.load_golden("c2_wm_as5_n10000")
+    zi, probi = helpers.regenerate_ensemble(g)
+    pot = helpers.potential_from_golden(g)
+    pr = propagators.WaltonManolopoulosPropagator(T(g['Gamma_i']), T(g['Gamma_t']), 500, 500, device=cuda_device)
+    pr.set_ensemble(T(g['q0']), T(g['p0']), T(g['Gamma_0']), T(zi), T(probi))
+    nt, e0, dt = int(g['nt']), float(g['energy0_es']), float(g['dt'])
+    auto, ic = [pr.autocorrelation(e0)], [pr.ic_correlation(pot, e0)]
+    l0 = pr.launch_count()
+    for k0 in range(0, nt - 1, 33):
+        a, i = pr.propagate(pot, dt, min(33, nt - 1 - k0), e0)
+        auto.extend(a)
+        ic.extend(i)
+    assert pr.kernel_name() == "k_hk_generic+k_wm_fused"
+    assert pr.launch_count() - l0 <= 3 * 5 + 3          # launches per 33 fused steps, not per step
+    assert relerr(auto, g['autocorrelation']) < TOL
+    assert relerr(ic, g['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    _check_wm_signs(pr, g)
+
+
 # ------------------------------------------------------------------ sGDML (config 5)
 # the kernel sum over training points is cancellation-prone: the reference's own gradient / Hessian move by
 # ~3e-9 (absolute) when the training set is summed in another order (SURVEY.md section 7.2-5); the kernel's
