@@ -158,6 +158,18 @@ int sc_engine_get_prefactor(sc_engine *eng, double *c_dev /* c128 (n) sqrt(det),
 int sc_engine_coefficients(sc_engine *eng, double *v_dev /* c128 (n) */, void *stream);
 int sc_engine_norm(sc_engine *eng, const double *A_host, const double *B_host, const double *C_host, double fac,
                    double *norm2_host /* [2] */, void *stream);
+/* norm() of an ensemble that is sharded over ranks (propagators.py:734-782 is all pairs of the GLOBAL ensemble; cli.py:424-429):
+ *   sc_engine_norm_pack   writes the ket vectors of this rank's shard into pack_dev (sc_engine_norm_pack_size doubles for
+ *                         n_pad >= n_local rows; layout [r | s | alphaJ | beta | coef]) and keeps the bra side in the engine
+ *   (caller)              all-gathers the packs of all ranks (NCCL)
+ *   sc_engine_norm_block  adds fac * sum_{i local} conj(v_i) sum_{j in pack} <i|j> v_j to norm2_host[0:2] for ONE rank's pack
+ *                         (n_ket = that rank's shard size); bra_coef_dev = coefficient section of this rank's own pack
+ *   (caller)              sums over the packs, all-reduces the two doubles over the ranks, takes sqrt(Re) */
+int sc_engine_norm_pack_size(const sc_engine *eng, int n_pad, long long *doubles_out);
+int sc_engine_norm_pack(sc_engine *eng, const double *A_host, const double *B_host, const double *C_host, int n_pad,
+                        double *pack_dev, void *stream);
+int sc_engine_norm_block(sc_engine *eng, int n_ket, int n_pad, const double *pack_dev, const double *bra_coef_dev, double fac,
+                         double *norm2_host, void *stream);
 int sc_engine_wavefunction(sc_engine *eng, const double *Gamma_t_host, double fac, int nx, const double *x_dev,
                            double *phi_dev /* c128 (nx) */, void *stream);
 int sc_engine_num_trajectories(const sc_engine *eng);

@@ -52,10 +52,26 @@ def build(force=False, verbose=False):
         return LIB_PATH
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH, os.path.join(CSRC, "sc_engine.cu")]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    # one builder at a time (torchrun starts every rank at once); the library is written next to its final place and
+    # renamed into it, so that no process can dlopen a half-written file
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not (force or needs_build()):      # another process built it while this one waited
+                return LIB_PATH
+            tmp = "%s.tmp.%d" % (LIB_PATH, os.getpid())
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp, os.path.join(CSRC, "sc_engine.cu")]
+            if verbose:
+                print(" ".join(cmd))
+            try:
+                subprocess.check_call(cmd)
+                os.replace(tmp, LIB_PATH)
+            finally:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -91,6 +107,9 @@ _SIGNATURES = {
     "sc_engine_num_trajectories": (ctypes.c_int, [_vp]),
     "sc_engine_coefficients": (ctypes.c_int, [_vp, _vp, _vp]),
     "sc_engine_norm": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _vp]),
+    "sc_engine_norm_pack_size": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
+    "sc_engine_norm_pack": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int, _vp, _vp]),
+    "sc_engine_norm_block": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp, ctypes.c_double, _vp, _vp]),
     "sc_engine_wavefunction": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, _vp]),
     "sc_engine_launch_count": (ctypes.c_longlong, [_vp]),
     "sc_engine_kernel_name": (ctypes.c_char_p, [_vp]),
@@ -117,6 +136,12 @@ def lib():
                 if not os.path.exists(LIB_PATH):
                     raise RuntimeError("semiclassical_b200: the CUDA library %s is missing and could not be built (%s); "
                                        "there is no CPU fallback" % (LIB_PATH, err))
+                # a library built from OLDER sources exists: using it silently would hide the failed build
+                if os.environ.get("SC_ALLOW_STALE_LIBRARY") != "1":
+                    raise RuntimeError("semiclassical_b200: %s is older than its sources and the rebuild failed (%s); "
+                                       "fix the build or set SC_ALLOW_STALE_LIBRARY=1 to load the stale library" % (LIB_PATH, err))
+                import warnings
+                warnings.warn("semiclassical_b200: loading a STALE CUDA library (rebuild failed: %s)" % (err,), RuntimeWarning)
         L = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)

@@ -34,6 +34,15 @@ static int fail(int code, const char *fmt, ...) {
   g_err = buf;
   return code;
 }
+// like CU inside the sc_potential_create_* functions: the half-built potential `p` is released before returning
+#define CUP(x)                                                                                     \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess) {                                                                       \
+      delete p;                                                                                    \
+      return fail(SC_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                              \
+  } while (0)
 #define CU(x)                                                                                      \
   do {                                                                                             \
     cudaError_t e_ = (x);                                                                          \
@@ -117,6 +126,8 @@ struct sc_engine {
   double *stream_const = nullptr;         // [H0 | L1 | L2], each d x ldh
   double *corr_dev = nullptr;
   size_t corr_cap = 0;
+  double *diag_scratch = nullptr, *pack_scratch = nullptr;   // wavefunction diagnostics: persistent scratch
+  size_t diag_cap = 0, pack_cap = 0;
   long long ntraj_norm = 0;
   int ens_n = 0;                  // size of the ensemble the buffers in `ens` were allocated for
   long long launches = 0;
@@ -131,6 +142,8 @@ struct sc_engine {
     if (chunk_scratch) cudaFree(chunk_scratch);
     if (stream_const) cudaFree(stream_const);
     if (wm.snap) cudaFree(wm.snap);
+    if (diag_scratch) cudaFree(diag_scratch);
+    if (pack_scratch) cudaFree(pack_scratch);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
 };
@@ -163,9 +176,9 @@ extern "C" int sc_potential_create_morse(sc_potential **out, int d, const double
   sc_potential *p = new sc_potential();
   int rc = pot_common(p, POT_MORSE, d, nullptr, nac);
   if (rc) { delete p; return rc; }
-  CU(p->pool.upload(omega, d, &p->dev.omega));
-  CU(p->pool.upload(a, d, &p->dev.a));
-  CU(p->pool.upload(D, d, &p->dev.D));
+  CUP(p->pool.upload(omega, d, &p->dev.omega));
+  CUP(p->pool.upload(a, d, &p->dev.a));
+  CUP(p->pool.upload(D, d, &p->dev.D));
   p->dev.all_harmonic = all_harmonic;
   *out = p;
   return SC_OK;
@@ -177,8 +190,11 @@ extern "C" int sc_potential_create_rotated_morse(sc_potential **out, int d, cons
   if (!Q) return fail(SC_ERR_INVALID, "null argument");
   int rc = sc_potential_create_morse(out, d, omega, a, D, all_harmonic, nac);
   if (rc) return rc;
-  (*out)->dev.type = POT_ROTATED_MORSE;
-  CU((*out)->pool.upload(Q, (size_t)d * d, &(*out)->dev.Q));
+  sc_potential *p = *out;
+  p->dev.type = POT_ROTATED_MORSE;
+  *out = nullptr;
+  CUP(p->pool.upload(Q, (size_t)d * d, &p->dev.Q));
+  *out = p;
   return SC_OK;
 }
 
@@ -188,8 +204,8 @@ extern "C" int sc_potential_create_nonharmonic(sc_potential **out, int d, const 
   sc_potential *p = new sc_potential();
   int rc = pot_common(p, POT_NONHARMONIC, d, nullptr, nullptr);  // masses 1, tau1 = 1
   if (rc) { delete p; return rc; }
-  CU(p->pool.upload(eps, d, &p->dev.eps));
-  CU(p->pool.upload(b, d, &p->dev.b));
+  CUP(p->pool.upload(eps, d, &p->dev.eps));
+  CUP(p->pool.upload(b, d, &p->dev.b));
   *out = p;
   return SC_OK;
 }
@@ -202,9 +218,9 @@ extern "C" int sc_potential_create_harmonic(sc_potential **out, int d, const dou
   sc_potential *p = new sc_potential();
   int rc = pot_common(p, POT_HARMONIC, d, masses, nac);
   if (rc) { delete p; return rc; }
-  CU(p->pool.upload(pos0, d, &p->dev.pos0));
-  CU(p->pool.upload(grad0, d, &p->dev.grad0));
-  CU(p->pool.upload(hess0, (size_t)d * d, &p->dev.hess0));
+  CUP(p->pool.upload(pos0, d, &p->dev.pos0));
+  CUP(p->pool.upload(grad0, d, &p->dev.grad0));
+  CUP(p->pool.upload(hess0, (size_t)d * d, &p->dev.hess0));
   p->dev.e0 = energy0;
   *out = p;
   return SC_OK;
@@ -220,8 +236,8 @@ extern "C" int sc_potential_create_gdml(sc_potential **out, int n_atoms, int n_t
   sc_potential *p = new sc_potential();
   int rc = pot_common(p, POT_GDML, d, masses, nac);
   if (rc) { delete p; return rc; }
-  CU(p->pool.upload(xs_train, (size_t)n_train * n_desc, &p->dev.xs_train));
-  CU(p->pool.upload(jx_alphas, (size_t)n_train * n_desc, &p->dev.jx_alphas));
+  CUP(p->pool.upload(xs_train, (size_t)n_train * n_desc, &p->dev.xs_train));
+  CUP(p->pool.upload(jx_alphas, (size_t)n_train * n_desc, &p->dev.jx_alphas));
   p->dev.n_atoms = n_atoms;
   p->dev.n_train = n_train;
   p->dev.n_desc = n_desc;
@@ -1260,21 +1276,44 @@ extern "C" int sc_engine_coefficients(sc_engine *e, double *v_dev, void *stream)
 
 // |psi|^2 = sum_ij conj(v_i) <q_i,p_i,Gt|q_j,p_j,Gt> v_j (HermanKlukPropagator.norm, propagators.py:734-782).  A, B, C: the
 // (d x d) matrices Gt (2 Gt)^+ Gt, (2 Gt)^+, Gt (2 Gt)^+ of CoherentStatesOverlap(Gt, Gt) (propagators.py:174-179), fac its
-// normalisation factor (:230).  norm2_host[0:2] = Re, Im of the double sum (rank-local when the ensemble is sharded: the
-// caller sums the (n_local x n_total) blocks).
-extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *B_host, const double *C_host, double fac,
-                              double *norm2_host, void *stream) {
-  if (!e || e->dev.n < 1 || !A_host || !B_host || !C_host || !norm2_host) return fail(SC_ERR_INVALID, "norm(): bad arguments");
+// normalisation factor (:230).
+// Sharded ensembles: every rank PACKS the ket vectors of its shard (sc_engine_norm_pack), the packs are all-gathered by the
+// caller (torch.distributed / NCCL), and every rank sums its (n_local x n_r) BLOCK against each rank's pack
+// (sc_engine_norm_block); the caller adds the blocks and all-reduces the two doubles.  Pack layout for n_pad rows:
+// [r (n_pad x kp) | s (n_pad x kp) | alphaJ (n_pad) | beta (n_pad) | coef (n_pad x 2)],  kp = (2 d + 3) & ~3.
+// The bra-side vectors stay in a persistent scratch of the engine (no allocation per call after the first).
+static int norm_scratch(sc_engine *e, size_t doubles, cudaStream_t st) {
+  if (doubles > e->diag_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->diag_scratch) cudaFree(e->diag_scratch);
+    e->diag_scratch = nullptr;
+    e->diag_cap = 0;
+    CU(cudaMalloc(&e->diag_scratch, sizeof(double) * doubles));
+    e->diag_cap = doubles;
+  }
+  return SC_OK;
+}
+
+extern "C" int sc_engine_norm_pack_size(const sc_engine *e, int n_pad, long long *doubles_out) {
+  if (!e || !doubles_out || n_pad < 1) return fail(SC_ERR_INVALID, "norm_pack_size(): bad arguments");
+  const int kp = (2 * e->dev.d + 3) & ~3;
+  *doubles_out = (long long)n_pad * (2 * kp + 4);
+  return SC_OK;
+}
+
+extern "C" int sc_engine_norm_pack(sc_engine *e, const double *A_host, const double *B_host, const double *C_host, int n_pad,
+                                   double *pack_dev, void *stream) {
+  if (!e || e->dev.n < 1 || !A_host || !B_host || !C_host || !pack_dev || n_pad < e->dev.n)
+    return fail(SC_ERR_INVALID, "norm_pack(): bad arguments");
   if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "norm(): Herman-Kluk propagator only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = e->dev.n, d = e->dev.d, kp = (2 * d + 3) & ~3;
-  DevBufs B;
-  double *mats, *a, *r, *s, *alpha, *beta, *gamma, *res;
-  double2 *v, *o;
-  CU(B.get(&mats, 3 * (size_t)d * d));
-  CU(B.get(&a, (size_t)n * kp)); CU(B.get(&r, (size_t)n * kp)); CU(B.get(&s, (size_t)n * kp));
-  CU(B.get(&alpha, n)); CU(B.get(&beta, n)); CU(B.get(&gamma, n)); CU(B.get(&res, 2));
-  CU(B.get(&v, n)); CU(B.get(&o, n));
+  // bra side: mats (3 d^2) | a (n kp) | alpha (n) | gamma (n) | o (2 n) | res (2)
+  const size_t m3 = (3 * (size_t)d * d + 1) & ~(size_t)1;
+  if (int rc = norm_scratch(e, m3 + (size_t)n * (kp + 4) + 8, st)) return rc;
+  double *mats = e->diag_scratch, *a = mats + m3, *alpha = a + (size_t)n * kp, *gamma = alpha + n;
+  double *r = pack_dev, *s = r + (size_t)n_pad * kp, *alphaJ = s + (size_t)n_pad * kp, *beta = alphaJ + n_pad;
+  double2 *v = reinterpret_cast<double2 *>(beta + n_pad);
   CU(cudaMemcpyAsync(mats, A_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(mats + d * d, B_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(mats + 2 * d * d, C_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
@@ -1282,16 +1321,59 @@ extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *
   CU(cudaGetLastError());
   k_gauss_prep_norm<<<n, 128, 0, st>>>(e->dev, mats, mats + d * d, mats + 2 * d * d, kp, a, r, s, alpha, beta, gamma);
   CU(cudaGetLastError());
-  CU(launch_gauss_sum(n, n, kp, a, alpha, gamma, r, s, alpha, beta, v, o, st));
-  k_gauss_dot<<<1, 256, 0, st>>>(n, v, o, res);
+  // the kets' alpha is the bras' alpha (same trajectories)
+  CU(cudaMemcpyAsync(alphaJ, alpha, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+  e->launches += 2;
+  return SC_OK;
+}
+
+// norm2_host[0:2] += fac * sum_{i local} conj(v_i) sum_{j < n_ket} O_ij v_j  for the kets of one pack.  bra_coef_dev: the
+// coefficient section of THIS rank's own pack (v_i)
+extern "C" int sc_engine_norm_block(sc_engine *e, int n_ket, int n_pad, const double *pack_dev, const double *bra_coef_dev,
+                                    double fac, double *norm2_host, void *stream) {
+  if (!e || e->dev.n < 1 || !pack_dev || !bra_coef_dev || !norm2_host || n_ket < 0 || n_ket > n_pad)
+    return fail(SC_ERR_INVALID, "norm_block(): bad arguments");
+  if (n_ket == 0) return SC_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n, d = e->dev.d, kp = (2 * d + 3) & ~3;
+  const size_t m3 = (3 * (size_t)d * d + 1) & ~(size_t)1;
+  if (e->diag_cap < m3 + (size_t)n * (kp + 4) + 8) return fail(SC_ERR_INVALID, "norm_block(): call sc_engine_norm_pack first");
+  double *mats = e->diag_scratch, *a = mats + m3, *alpha = a + (size_t)n * kp, *gamma = alpha + n;
+  double2 *o = reinterpret_cast<double2 *>(gamma + n);
+  double *res = reinterpret_cast<double *>(o + n);
+  const double *r = pack_dev, *s = r + (size_t)n_pad * kp, *alphaJ = s + (size_t)n_pad * kp, *beta = alphaJ + n_pad;
+  const double2 *v = reinterpret_cast<const double2 *>(beta + n_pad);
+  CU(launch_gauss_sum(n, n_ket, kp, a, alpha, gamma, r, s, alphaJ, beta, v, o, st));
+  k_gauss_dot<<<1, 256, 0, st>>>(n, reinterpret_cast<const double2 *>(bra_coef_dev), o, res);
   CU(cudaGetLastError());
   double h[2];
   CU(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  norm2_host[0] = fac * h[0];
-  norm2_host[1] = fac * h[1];
-  e->launches += 4;
+  norm2_host[0] += fac * h[0];
+  norm2_host[1] += fac * h[1];
+  e->launches += 2;
   return SC_OK;
+}
+
+// single-rank convenience: pack + one block
+extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *B_host, const double *C_host, double fac,
+                              double *norm2_host, void *stream) {
+  if (!e || e->dev.n < 1 || !norm2_host) return fail(SC_ERR_INVALID, "norm(): bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n, kp = (2 * e->dev.d + 3) & ~3;
+  const size_t packsz = (size_t)n * (2 * kp + 4);
+  if (packsz > e->pack_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->pack_scratch) cudaFree(e->pack_scratch);
+    e->pack_scratch = nullptr;
+    e->pack_cap = 0;
+    CU(cudaMalloc(&e->pack_scratch, sizeof(double) * packsz));
+    e->pack_cap = packsz;
+  }
+  if (int rc = sc_engine_norm_pack(e, A_host, B_host, C_host, n, e->pack_scratch, stream)) return rc;
+  norm2_host[0] = norm2_host[1] = 0.0;
+  const double *coef = e->pack_scratch + (size_t)n * (2 * kp + 2);
+  return sc_engine_norm_block(e, n, n, e->pack_scratch, coef, fac, norm2_host, stream);
 }
 
 // psi(x_k) = sum_i v_i <x_k|q_i,p_i,Gt> on nx grid points (HermanKlukPropagator.wavefunction, propagators.py:688-732);

@@ -41,3 +41,22 @@ def rows_to_correlations(rows, times, energy0_es, hbar=1.0):
     rows = rows.detach().cpu().numpy() if isinstance(rows, torch.Tensor) else np.asarray(rows)
     phase = np.exp(1j / hbar * np.asarray(times) * energy0_es)
     return (rows[:, 0] + 1j * rows[:, 1]) * phase, (rows[:, 2] + 1j * rows[:, 3]) * phase
+
+
+def agree_on_error(err, device='cpu', group=None):
+    """
+    collective error handling of the task driver: a failure on ONE rank (file validation, empty shard, energy guard, NaN
+    guard) raises on EVERY rank before the next collective instead of leaving the others blocked in it.  `err` is the
+    exception this rank caught (or None); the failing rank re-raises its own exception, the others a RuntimeError.
+    """
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if err is not None:
+            raise err
+        return
+    flag = torch.tensor([0.0 if err is None else 1.0], dtype=torch.float64, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if float(flag.item()) > 0.0:
+        if err is not None:
+            raise err
+        raise RuntimeError("semi dynamics: another rank failed (see its log); stopping all ranks")

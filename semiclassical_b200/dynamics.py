@@ -82,6 +82,19 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
+    device = torch.device(device)
+    if device.type == 'cuda' and device.index is None and world > 1:
+        device = torch.device('cuda', torch.cuda.current_device())
+
+    def agree(err):
+        distributed.agree_on_error(err, device)
+
+    def guarded(fn):
+        try:
+            return fn(), None
+        except Exception as err:   # noqa: BLE001 -- re-raised on all ranks by agree()
+            return None, err
+
     p = task['potential']
     excited_fchk = None
     if p['type'] in ("harmonic", "gdml"):
@@ -98,15 +111,22 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
 
     dt = task['time_step_fs'] / units.autime_to_fs
     nt = task['num_steps']
-    times = torch.linspace(0.0, nt * dt, nt)
+    # explicit dtypes: the reference relies on torch.set_default_dtype(float64) in its CLI (cli.py:121); this driver must
+    # produce the same float64 grid (and pass the overwrite=False array_equal check) whatever the process-wide default is
+    times = torch.linspace(0.0, nt * dt, nt, dtype=torch.float64)
     batch_size = task.get('batch_size', 10000)
     num_trajectories = task.get('num_trajectories', 50000)
     num_repetitions = max(num_trajectories // batch_size, 1)
     num_samples = min(batch_size, num_trajectories)
     propagator_name = task.get('propagator', 'HK')
+    if num_samples < world:
+        raise ConfigurationError(f"{num_samples} trajectories per repetition cannot be sharded over {world} ranks")
+    if world > 1 and not getattr(potential, '_fused_step', True):
+        raise ConfigurationError("this potential is evaluated through the stage interface and cannot be sharded over ranks")
 
     filename = task['results'].get('correlations', 'correlations.npz')
-    if rank == 0:
+
+    def prepare_file():
         if task['results'].get('overwrite', True) is True or (not os.path.exists(filename)):
             np.savez(filename, propagator=propagator_name, times=times, autocorrelation=np.zeros((nt,), dtype=complex),
                      ic_correlation=np.zeros((nt,), dtype=complex), adiabatic_gap=adiabatic_gap, zero_point_energy=en_zpt,
@@ -118,6 +138,9 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
             assert np.array_equal(data['times'], times.numpy()), \
                 f"Time steps in {filename} differ. Delete the old file or change the grid for time propagation."
             assert data['propagator'] == propagator_name, "Data produced with different propagators cannot be added."
+
+    _, err = guarded(prepare_file) if rank == 0 else (None, None)
+    agree(err)
     seed = task.get('manual_seed', None)
     if seed is not None:
         logger.warning("The random number generator should not be seeded manually unless for debugging!")
@@ -133,42 +156,69 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
         propagator = propagators.WaltonManolopoulosPropagator(Gamma_i, Gamma_t, alpha, alpha, device=device)
     else:
         propagator = propagators.HermanKlukPropagator(Gamma_i, Gamma_t, device=device)
+    norm_warned = False
     for repetition in range(num_repetitions):
         logger.info(f"*** Repetition {repetition+1} ***")
         lo, hi = distributed.shard_bounds(num_samples, rank, world)
-        if ensembles is not None:
-            zi, probi = ensembles[repetition]
-            propagator.set_ensemble(q0, p0, Gamma_0, torch.as_tensor(zi)[:, lo:hi], torch.as_tensor(probi)[lo:hi],
-                                    ntraj_total=num_samples)
-        else:
-            propagator.initial_conditions(q0, p0, Gamma_0, ntraj=hi - lo, ntraj_total=num_samples)
+
+        def install():
+            if ensembles is not None:
+                zi, probi = ensembles[repetition]
+                propagator.set_ensemble(q0, p0, Gamma_0, torch.as_tensor(zi)[:, lo:hi], torch.as_tensor(probi)[lo:hi],
+                                        ntraj_total=num_samples)
+            else:
+                propagator.initial_conditions(q0, p0, Gamma_0, ntraj=hi - lo, ntraj_total=num_samples)
+        _, err = guarded(install)
+        agree(err)
         autocorrelation_ = np.zeros((nt,), dtype=complex)
         ic_correlation_ = np.zeros((nt,), dtype=complex)
         # t = 0 from the installed ensemble, then fused launches; a launch ends where the norm is due
-        first = torch.tensor([complex(propagator.autocorrelation(energy0_es=en_zpt)),
-                              complex(propagator.ic_correlation(potential, energy0_es=en_zpt))], device=propagator.device)
+        first = torch.tensor([[0.0, 0.0], [0.0, 0.0]], dtype=torch.float64, device=propagator.device)
+
+        def first_values():
+            c0 = complex(propagator.autocorrelation(energy0_es=en_zpt))
+            k0 = complex(propagator.ic_correlation(potential, energy0_es=en_zpt))
+            first[0, 0], first[0, 1], first[1, 0], first[1, 1] = c0.real, c0.imag, k0.real, k0.imag
+        _, err = guarded(first_values)
+        agree(err)
         if world > 1:
-            first = torch.view_as_real(first).contiguous()
             dist.all_reduce(first)
-            first = torch.view_as_complex(first)
-        autocorrelation_[0], ic_correlation_[0] = (complex(x) for x in first.cpu().numpy())
+        fh = first.cpu().numpy()
+        autocorrelation_[0], ic_correlation_[0] = complex(fh[0, 0], fh[0, 1]), complex(fh[1, 0], fh[1, 1])
         t = 0
         while True:
-            if calc_norm_every > 0 and t % calc_norm_every == 0 and world == 1:
-                norm = propagator.norm()
-                logger.info(f" time/fs= {times[t]*units.autime_to_fs}  norm= {norm:9.6f}")
+            if calc_norm_every > 0 and t % calc_norm_every == 0:
+                # all pairs of the GLOBAL ensemble (cli.py:424-429); sharded: ket vectors all-gathered, blocks all-reduced
+                norm, err = guarded(lambda: propagator.norm(group=group))
+                if isinstance(err, NotImplementedError):
+                    if not norm_warned:
+                        logger.warning(f"norm() is not available for this propagator ({err}); calc_norm_every is ignored")
+                        norm_warned = True
+                    err = None
+                    if world > 1:
+                        # the failing call skipped its collectives on every rank alike (the decision is rank independent)
+                        pass
+                agree(err)
+                if norm is not None:
+                    logger.info(f" time/fs= {times[t]*units.autime_to_fs}  norm= {norm:9.6f}")
             if t == nt - 1:
                 break
             k = min(steps_per_launch, nt - 1 - t)
             if calc_norm_every > 0:
                 k = min(k, calc_norm_every - t % calc_norm_every)
-            a, i = propagator.propagate(potential, dt, k, energy0_es=en_zpt, group=group)
-            autocorrelation_[t + 1:t + 1 + k], ic_correlation_[t + 1:t + 1 + k] = a, i
+
+            def launch():
+                a, i = propagator.propagate(potential, dt, k, energy0_es=en_zpt, group=group)
+                assert not np.isnan(a).any(), f"encountered NaN's in autocorrelation : {a}"
+                assert not np.isnan(i).any(), f"encountered NaN's in IC correlation : {i}"
+                return a, i
+            res, err = guarded(launch)
+            agree(err)
+            autocorrelation_[t + 1:t + 1 + k], ic_correlation_[t + 1:t + 1 + k] = res
             t += k
-            assert not np.isnan(autocorrelation_).any(), f"encountered NaN's in autocorrelation : {autocorrelation_}"
-            assert not np.isnan(ic_correlation_).any(), f"encountered NaN's in IC correlation : {ic_correlation_}"
         # the last step() of the reference loop only advances the state, its correlations are never read (cli.py:436)
-        if rank == 0:
+
+        def accumulate():
             data = dict(np.load(filename))
             ntraj_old, ntraj_new = data['trajectories'], num_samples
             ntraj_tot = ntraj_old + ntraj_new
@@ -181,4 +231,12 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
             data['ic_correlation'] = ic_correlation
             data.pop('ic_rate', None)
             np.savez(filename, **data)
+            return data
+        data, err = guarded(accumulate) if rank == 0 else (None, None)
+        agree(err)
+    if world > 1:
+        # every rank returns the arrays rank 0 wrote
+        box = [data]
+        dist.broadcast_object_list(box, src=0)
+        data = box[0]
     return data

@@ -530,18 +530,65 @@ class HermanKlukPropagator(object):
                                                                self._stream()))
         return phi.detach().cpu().numpy()
 
-    def norm(self):
+    def norm(self, group=None):
         """
         norm |psi| = sqrt(sum_ij v_i^* v_j <g_i|g_j>) of the frozen Gaussian wavefunction (propagators.py:734-782);
-        all pairs of trajectories, O(ntraj^2), as two FP64 tensor-core contractions + exp/sincos per pair
+        all pairs of trajectories, O(ntraj^2), as two FP64 tensor-core contractions + exp/sincos per pair.
+
+        group : torch.distributed process group (or True for the default group) when this propagator holds one shard of a
+                global ensemble: the ket vectors of all shards are all-gathered, every rank sums its
+                (n_local x n_total) block of pairs, and the blocks are all-reduced -- the norm of the GLOBAL wavefunction
+                on every rank (cli.py:424-429 computes it on the one process that holds everything)
         """
         cs = CoherentStatesOverlap(self.Gamma_t, self.Gamma_t)
         A, B, C = _np(cs.Gi_iGij_Gj), _np(cs.iGij), _np(cs.Gj_iGij)
         out = np.zeros(2)
+        L = _native.lib()
+        if group is None:
+            with torch.cuda.device(self.device):
+                _native.check(L.sc_engine_norm(self._engine, _ptr(A), _ptr(B), _ptr(C), float(cs.fac), _ptr(out), self._stream()))
+            return float(np.sqrt(out[0]))
+        import torch.distributed as dist
+        pg = None if group is True else group
+        world, rank = dist.get_world_size(pg), dist.get_rank(pg)
+        counts = torch.zeros(world, dtype=torch.int64, device=self.device)
+        counts[rank] = self.ntraj
+        dist.all_reduce(counts, group=pg)
+        counts = [int(c) for c in counts.cpu()]
+        n_pad = max(counts)
+        pack = self.norm_pack(n_pad)
+        packs = torch.empty(world * pack.numel(), dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(packs, pack, group=pg)
+        tot = 0.0j
+        for r in range(world):
+            tot += self.norm_block(packs[r * pack.numel():(r + 1) * pack.numel()], counts[r], n_pad, pack)
+        tot = torch.tensor([tot.real, tot.imag], dtype=torch.float64, device=self.device)
+        dist.all_reduce(tot, group=pg)
+        return float(np.sqrt(float(tot[0])))
+
+    def norm_pack(self, n_pad):
+        """ket vectors of this shard for the sharded norm (include/semiclassical_b200.h: sc_engine_norm_pack); 1-D fp64 tensor"""
+        cs = CoherentStatesOverlap(self.Gamma_t, self.Gamma_t)
+        A, B, C = _np(cs.Gi_iGij_Gj), _np(cs.iGij), _np(cs.Gj_iGij)
+        self._norm_fac = float(cs.fac)
+        size = ctypes.c_longlong()
+        L = _native.lib()
+        _native.check(L.sc_engine_norm_pack_size(self._engine, n_pad, ctypes.byref(size)))
+        pack = torch.zeros(size.value, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _native.check(_native.lib().sc_engine_norm(self._engine, _ptr(A), _ptr(B), _ptr(C), float(cs.fac), _ptr(out),
-                                                       self._stream()))
-        return float(np.sqrt(out[0]))
+            _native.check(L.sc_engine_norm_pack(self._engine, _ptr(A), _ptr(B), _ptr(C), n_pad, pack.data_ptr(), self._stream()))
+        return pack
+
+    def norm_block(self, other_pack, n_ket, n_pad, own_pack):
+        """sum_{i in this shard} conj(v_i) sum_{j in other_pack} <g_i|g_j> v_j  (complex); norm_pack() must have been called"""
+        kp = (2 * self.dim + 3) & ~3
+        out = np.zeros(2)
+        other_pack = other_pack.contiguous()
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().sc_engine_norm_block(self._engine, int(n_ket), int(n_pad), other_pack.data_ptr(),
+                                                             own_pack.data_ptr() + 8 * n_pad * (2 * kp + 2), self._norm_fac,
+                                                             _ptr(out), self._stream()))
+        return complex(out[0], out[1])
 
     def set_option(self, name, value):
         """engine run-time options (include/semiclassical_b200.h: sc_engine_set_option), e.g. 'dense_engine'"""

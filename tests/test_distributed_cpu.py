@@ -73,3 +73,39 @@ def test_two_ranks_reproduce_the_unsharded_run(name, tmp_path):
     pot, consts, wm = oracle.from_golden(g)
     full = oracle.run(pot, consts, g['zi'], g['probi'], float(g['dt']), nt, float(g['energy0_es']), wm=wm)
     assert np.abs(res['energy'] - full['energy']).max() < 1e-12 * max(1.0, np.abs(full['energy']).max())
+
+
+def _agree_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        seen = []
+        # round 1: nobody failed -> nobody raises; round 2: rank 1 failed -> BOTH ranks raise before the next collective
+        distributed.agree_on_error(None)
+        seen.append("ok")
+        try:
+            distributed.agree_on_error(ValueError("energy guard on rank 1") if rank == 1 else None)
+            seen.append("no exception")
+        except ValueError as err:
+            seen.append("own:" + str(err))
+        except RuntimeError as err:
+            seen.append("peer:" + str(err)[:40])
+        # the ranks are still in lock step: one more collective completes
+        t = torch.ones(1)
+        dist.all_reduce(t)
+        seen.append(int(t.item()))
+        with open(out + str(rank), "w") as f:
+            f.write(repr(seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_error_on_one_rank_raises_on_all(tmp_path):
+    """a rank that raises (validation, energy guard) must not leave the others blocked in the next all-reduce"""
+    out = str(tmp_path / "seen")
+    mp.spawn(_agree_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    s0, s1 = (eval(open(out + str(r)).read()) for r in (0, 1))
+    assert s0[0] == "ok" and s1[0] == "ok"
+    assert s0[1].startswith("peer:") and s1[1] == "own:energy guard on rank 1"
+    assert s0[2] == 2 and s1[2] == 2

@@ -372,6 +372,26 @@ def test_wavefunction_diagnostics_match_reference(name, cuda_device):
     assert relerr(phi, g['wavefunction']) < TOL
 
 
+def test_sharded_norm_blocks_add_up(cuda_device):
+    """norm() of a sharded ensemble (propagators.py:734-782 is all pairs of the GLOBAL ensemble): two shards on one device,
+    the four (n_a x n_b) blocks through sc_engine_norm_pack / sc_engine_norm_block add up to the reference's norm"""
+    g = helpers.load_golden("diag_as24")
+    pot = helpers.potential_from_golden(g)
+    n = len(g['probi'])
+    cut = 57
+    shards = [helpers.propagator_from_golden(g, cuda_device, nslice=sl) for sl in (slice(0, cut), slice(cut, n))]
+    for pr in shards:
+        pr.propagate(pot, float(g['dt']), int(g['nt']), float(g['energy0_es']))
+    n_pad = max(pr.ntraj for pr in shards)
+    packs = [pr.norm_pack(n_pad) for pr in shards]
+    tot = 0.0j
+    for a, pa in enumerate(shards):
+        for b, pb in enumerate(shards):
+            tot += pa.norm_block(packs[b], pb.ntraj, n_pad, packs[a])
+    assert abs(tot.imag) < 1.0e-12 * abs(tot.real)
+    assert abs(np.sqrt(tot.real) / float(g['norm']) - 1.0) < TOL
+
+
 def test_norm_against_oracle_ragged(cuda_device):
     """norm() on an ensemble that is not a multiple of the 64 x 32 tile (n = 203, d = 40: K = 80) vs the numpy oracle"""
     from oracle import oracle
