@@ -31,7 +31,8 @@ extern "C" {
 #define SC_ERR_UNSUPPORTED 3  /* configuration outside the kernels' envelope -> NotImplementedError */
 
 #define SC_ABI_VERSION 1
-#define SC_MAX_DIM 64         /* largest number of degrees of freedom the fused kernels accept */
+#define SC_MAX_DIM 96         /* largest number of degrees of freedom: separable / rotated / sGDML potentials d <= 64,
+                                 harmonic potentials (dense column pipeline with several CTAs per trajectory) d <= 96 */
 #define SC_TIMING_SLOTS 8     /* per-kernel timing slots: path, rk4, lu, finish, rmult, potential Hessians */
 
 typedef struct sc_potential sc_potential; /* opaque: device-resident potential parameters */

@@ -667,8 +667,15 @@ static int stream_setup(sc_engine *e, StreamLayout &L, cudaStream_t st) {
   const int d = e->dev.d, dr = e->dev.dr;
   int ns = 3;
   if (const char *s = getenv("SC_STREAM_SLOTS")) ns = std::max(2, std::min(4, atoi(s)));
-  L = make_stream_layout(d, dr, 2, ns);
-  while (L.ns > 2 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 2, L.ns - 1);
+  if (d <= 64) {
+    L = make_stream_layout(d, dr, 2, ns);
+    while (L.ns > 2 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 2, L.ns - 1);
+  } else {
+    // one tile per warp, as many warps (<= 8) as fit next to a double-buffered Hessian ring; several CTAs per trajectory
+    int nw = 8;
+    L = make_stream_layout(d, dr, 1, 2, nw);
+    while (nw > 1 && sizeof(double) * (size_t)L.total > 226 * 1024) L = make_stream_layout(d, dr, 1, 2, --nw);
+  }
   if (sizeof(double) * (size_t)L.total > 227 * 1024)
     return fail(SC_ERR_UNSUPPORTED, "stream pipeline: %zu B of shared memory (d = %d)", sizeof(double) * (size_t)L.total, d);
   const size_t hsz = (size_t)L.hsz;
@@ -724,7 +731,7 @@ static int run_prefactor_stream(sc_engine *e, int mode, cudaStream_t st) {
   none.imass = e->dev.q0;
   for (long long t0 = 0; t0 < n; t0 += ntb) {
     const int nt = (int)std::min<long long>(ntb, n - t0);
-    CU(launch_stream(std::min(nt, sm), e->dev, none, 0.0, 1, (int)t0, nt, A, L, st));
+    CU(launch_stream((int)std::min<long long>((long long)nt * L.ngroups, sm), e->dev, none, 0.0, 1, (int)t0, nt, A, L, st));
     if (dense) CU(launch_rmult(e->dev, nt, A.T, cm, sm, st));
     CU(launch_lu_batch(cm, dr, nt, det, sm, 0, st));
     k_track_only<<<(nt + 127) / 128, 128, 0, st>>>(e->dev, (int)t0, nt, det, mode == MODE_INIT ? 1 : 0);
@@ -846,7 +853,7 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
         e->launches += 1;
       }
       timing_mark(e, TS_RK4, st);
-      CU(launch_stream(std::min(nt, sm), e->dev, P, h, ks, (int)t0, nt, A, L, st));
+      CU(launch_stream((int)std::min<long long>((long long)nt * L.ngroups, sm), e->dev, P, h, ks, (int)t0, nt, A, L, st));
       if (dense) {
         timing_mark(e, TS_RMULT, st);
         CU(launch_rmult(e->dev, (long long)ks * nt, T, cm, sm, st));
@@ -865,8 +872,10 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
   e->launches += 1;
-  e->kernel_name = dense ? (dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_batch+k_hk_finish")
-                         : (dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_batch+k_hk_finish");
+  e->kernel_name = dense ? (dr > 64 ? "k_rk4_stream+k_rmult+k_lu_big+k_hk_finish"
+                                    : dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_batch+k_hk_finish")
+                         : (dr > 64 ? "k_rk4_stream+k_lu_big+k_hk_finish"
+                                    : dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_batch+k_hk_finish");
   return SC_OK;
 }
 
@@ -1306,6 +1315,7 @@ extern "C" int sc_engine_norm_pack(sc_engine *e, const double *A_host, const dou
   if (!e || e->dev.n < 1 || !A_host || !B_host || !C_host || !pack_dev || n_pad < e->dev.n)
     return fail(SC_ERR_INVALID, "norm_pack(): bad arguments");
   if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "norm(): Herman-Kluk propagator only");
+  if (gs_smem_bytes((2 * e->dev.d + 3) & ~3) > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "norm(): d = %d exceeds the all-pairs kernel's tiles (d <= 64)", e->dev.d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = e->dev.n, d = e->dev.d, kp = (2 * d + 3) & ~3;
   // bra side: mats (3 d^2) | a (n kp) | alpha (n) | gamma (n) | o (2 n) | res (2)

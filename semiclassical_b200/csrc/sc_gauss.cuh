@@ -22,7 +22,7 @@
 namespace sc {
 
 constexpr int GS_TI = 64, GS_TJ = 32, GS_THREADS = 256;
-constexpr int SC_MAX_DIM_DEV = 64;     // = SC_MAX_DIM of the C ABI
+constexpr int SC_MAX_DIM_DEV = 96;     // = SC_MAX_DIM of the C ABI
 
 __host__ __device__ constexpr int gs_ld(int kp) { return kp % 16 == 4 || kp % 16 == 12 ? kp : ((kp + 4) % 16 == 4 || (kp + 4) % 16 == 12 ? kp + 4 : kp + 8); }
 

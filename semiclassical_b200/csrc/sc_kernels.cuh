@@ -14,7 +14,7 @@
 #pragma once
 #include "sc_device.cuh"
 #ifndef SC_MAX_DIM
-#define SC_MAX_DIM 64
+#define SC_MAX_DIM 96
 #endif
 
 namespace sc {

@@ -54,10 +54,41 @@ k_lu_left(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restric
   }
 }
 
-// dr <= 64.  NW x NBLK x 4 >= dr
+// dr > 64 (harmonic molecules with more than 21 atoms): one CTA per matrix, the matrix in shared memory, Gaussian elimination
+// with implicit partial pivoting (lu_det, sc_device.cuh).  Correct for any dr whose matrix fits (dr <= 118); the tuned
+// kernels above hold rows in 64-bit masks / 64-row register tiles and stop at dr = 64.
+__global__ void __launch_bounds__(256)
+k_lu_big(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restrict__ det_out) {
+  extern __shared__ __align__(16) unsigned char lub_smem[];
+  double2 *Cm = reinterpret_cast<double2 *>(lub_smem);
+  double2 *pivbuf = Cm + (size_t)dr * dr;
+  int *ibuf = reinterpret_cast<int *>(pivbuf + 2);
+  const int t = threadIdx.x;
+  for (int mat = blockIdx.x; mat < nmat; mat += gridDim.x) {
+    const double2 *A = mats + (size_t)mat * dr * dr;
+    __syncthreads();
+    for (int i = t; i < dr * dr; i += 256) Cm[i] = A[i];
+    __syncthreads();
+    const double2 det = lu_det<256>(Cm, dr, ibuf, pivbuf, t, 0);
+    if (t == 0) det_out[mat] = det;
+  }
+}
+
+// NW x NBLK x 4 >= dr for the tuned kernels (dr <= 64)
 static cudaError_t launch_lu_batch(const double2 *mats, int dr, int nmat, double2 *det_out, int sm_count, int ctas_per_sm,
                                    cudaStream_t st) {
   if (nmat <= 0) return cudaSuccess;
+  if (dr > 64) {
+    const size_t smem = sizeof(double2) * ((size_t)dr * dr + 2) + sizeof(int) * (2 * (size_t)dr + 4);
+    cudaError_t ce = cudaFuncSetAttribute(k_lu_big, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int grid = sm_count * per_sm;
+    if (grid > nmat) grid = nmat;
+    k_lu_big<<<grid, 256, smem, st>>>(mats, dr, nmat, det_out);
+    return cudaGetLastError();
+  }
   if (dr > 32 && !getenv("SC_LU_DFMA")) {
     // trailing updates on the FP64 tensor pipe (sc_lu_mma.cuh); 3 matrices per SM (60 KB of panels each at dr = 60)
     const size_t smem = lum_smem_bytes(dr);

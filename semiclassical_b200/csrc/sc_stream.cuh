@@ -33,15 +33,17 @@
 namespace sc {
 
 struct StreamLayout {
-  int nt, ntw, nwarp, dk, ldh, hsz, ns, mtr;     // tiles, tiles per warp, warps, padded K, ld / size of a stream matrix, slots
+  int nt, ntw, nwarp, ngroups, dk, ldh, hsz, ns, mtr;   // tiles, tiles per warp, warps per CTA, CTAs (tile groups) per trajectory, ...
   int off_ring, off_c, off_W, slab, wstride, total;   // doubles
 };
 
-__host__ __device__ inline StreamLayout make_stream_layout(int d, int dr, int ntw, int ns) {
+// nwarp = 0: one CTA holds all tiles of a trajectory; else nwarp warps per CTA and ceil(nt / (nwarp ntw)) CTAs per trajectory
+__host__ __device__ inline StreamLayout make_stream_layout(int d, int dr, int ntw, int ns, int nwarp = 0) {
   StreamLayout L;
   L.nt = (d + 3) / 4;
   L.ntw = ntw;
-  L.nwarp = (L.nt + ntw - 1) / ntw;
+  L.nwarp = nwarp > 0 ? nwarp : (L.nt + ntw - 1) / ntw;
+  L.ngroups = (L.nt + L.nwarp * ntw - 1) / (L.nwarp * ntw);
   L.dk = (d + 3) & ~3;
   L.ldh = cols_ldh(L.dk / 4);
   L.hsz = d * L.ldh;
@@ -70,12 +72,13 @@ struct StreamArgs {
 };
 
 // ------------------------------------------------------------------ matrix kernel
+constexpr int stream_max_threads(int nk, int ntw) { return nk <= 16 ? 32 * ((nk + ntw - 1) / ntw) : 256; }
+
 template <int NK, int NTW>
-__global__ void __launch_bounds__(32 * ((NK + NTW - 1) / NTW), 1)
+__global__ void __launch_bounds__(stream_max_threads(NK, NTW), 1)
 k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, StreamArgs A, StreamLayout L) {
   constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
   constexpr int LDH = cols_ldh(NK), DK = 4 * NK;
-  constexpr int NWARP = (NK + NTW - 1) / NTW;
   constexpr int SLAB = DK * 8, SLAB2 = SLAB / 2;
   constexpr int MAXS = 4;
   extern __shared__ __align__(16) double smem[];
@@ -83,7 +86,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   __shared__ int cnt[MAXS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int d = E.d, dp = (d + 1) & ~1, dr = E.dr;
-  const int NS = L.ns, hsz = L.hsz;
+  const int NS = L.ns, hsz = L.hsz, nwarps = (int)(blockDim.x >> 5), ngroups = L.ngroups;
   const bool dense = A.T != nullptr;
   const int nrk = A.skip_rk4 ? 0 : 4;
   const int nstg = nrk + (dense ? 2 : 0);
@@ -116,7 +119,8 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       c[4 * dp + a] = a < d ? P.imass[a] : 0.0;
     }
   }
-  const int n_iter = (ntb - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const long long nitems = (long long)ntb * ngroups;       // item = (trajectory, tile group)
+  const int n_iter = (int)((nitems - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x);
   const int per_traj = nsteps * nstg;
   const long long G = (long long)n_iter * per_traj;
   const int per_traj_d = per_traj > 0 ? per_traj : 1;
@@ -124,7 +128,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
     if (g >= G) return;
     const int it = (int)(g / per_traj_d), rem = (int)(g - (long long)it * per_traj_d);
     const int step = rem / nstg, sidx = rem - step * nstg + (4 - nrk);
-    const int tl = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tl = (int)(((long long)blockIdx.x + (long long)it * gridDim.x) / ngroups);
     const double *src;
     if (sidx < 4) src = A.hs_const ? A.hs : A.hs + ((size_t)(step * 4 + sidx) * ntb + tl) * hsz;
     else src = (sidx == 4) ? A.L1p : A.L2p;
@@ -139,9 +143,10 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
 
   long long g = 0;
   // wait for stage g, acc = A_g B (B: this warp's U or V slabs), release the slot
-  auto mma_stage = [&](const double *__restrict__ Bb, bool two, double (&acc)[NTW][MT][2]) {
+  auto mma_stage = [&](const double *__restrict__ Bb, bool valid, bool two, double (&acc)[NTW][MT][2]) {
     const int slot = (int)(g % NS);
     mbar_wait(&full[slot], (uint32_t)((g / NS) & 1));
+    if (valid) {
     const double *__restrict__ Hs = ring + (size_t)slot * hsz + fc;
     const double *__restrict__ Hfr0 = Hs + fr * LDH, *__restrict__ Hfrl = Hs + frl * LDH;
 #pragma unroll
@@ -164,11 +169,12 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
         for (int i = 0; i < MT; ++i) dmma884(acc[NTW - 1][i][0], acc[NTW - 1][i][1], af[i], bf[NTW - 1]);
       }
     }
+    }
     __syncwarp();
     if (lane == 0) {
       __threadfence_block();
       const int old = atomicAdd(&cnt[slot], 1);
-      if (old == NWARP - 1) {                           // every warp is done with the slot: refill it
+      if (old == nwarps - 1) {                           // every warp is done with the slot: refill it
         cnt[slot] = 0;
         __threadfence_block();
         issue(g + NS);
@@ -178,16 +184,19 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   };
 
   for (int it = 0; it < n_iter; ++it) {
-    const int tl = (int)blockIdx.x + it * (int)gridDim.x;
+    const long long item = (long long)blockIdx.x + (long long)it * gridDim.x;
+    const int tl = (int)(item / ngroups), grp = (int)(item - (long long)tl * ngroups);
     const int traj = traj0 + tl;
+    const int tile0 = (grp * nwarps + warp) * NTW;          // first column tile of this warp
+    const bool valid = tile0 < NK;                          // warp-uniform: the last group of a trajectory may be ragged
     int b[NTW];
     bool bok[NTW];
 #pragma unroll
     for (int w = 0; w < NTW; ++w) {
-      b[w] = 4 * (NTW * warp + w) + fc;                     // the column b this thread's elements of tile w belong to
-      bok[w] = b[w] < d;
+      b[w] = 4 * (tile0 + w) + fc;                          // the column b this thread's elements of tile w belong to
+      bok[w] = valid && b[w] < d;
     }
-    const bool two = NTW > 1 && (NTW * warp + 1 < NK);      // warp-uniform: the second tile exists
+    const bool two = NTW > 1 && (tile0 + 1 < NK);           // warp-uniform: the second tile exists
     double *rec = E.rec + (size_t)traj * E.rs;
     __syncwarp();
     // ---- load the slabs: row a = 8 i + fr, element pair (2 fc, 2 fc + 1) = (q-half, p-half) of column b
@@ -198,7 +207,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       for (int i = 0; i < MT; ++i) {
         const int a = 8 * i + fr;
         u[i] = v[i] = make_double2(0.0, 0.0);
-        if (a < d && bok[w]) {
+        if (a < d && bok[w] && (w == 0 || two)) {
           const double *ru = rec + E.qps + (size_t)a * 2 * d, *rv = ru + 2 * d * d;
           u[i] = make_double2(ru[b[w]], ru[d + b[w]]);
           v[i] = make_double2(rv[b[w]], rv[d + b[w]]);
@@ -221,11 +230,11 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       const size_t mat = (size_t)step * ntb + tl;
 #pragma unroll 1
       for (int s = 1; s <= nrk; ++s) {
-        mma_stage(Ub, two, acc);
+        mma_stage(Ub, valid, two, acc);
         // ---- RK4 bookkeeping on the warp's own slabs, stage operand in place
 #pragma unroll
         for (int w = 0; w < NTW; ++w) {
-          if (w > 0 && !two) break;
+          if (!valid || (w > 0 && !two)) break;
           double2 *Uw = Uo + w * 2 * SLAB2, *Vw = Uw + SLAB2;
           if (s == 1) {
 #pragma unroll
@@ -286,11 +295,11 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
         const int mtr = L.mtr;
 #pragma unroll 1
         for (int pl = 0; pl < 2; ++pl) {
-          mma_stage(Ub + pl * SLAB, two, acc);
+          mma_stage(Ub + pl * SLAB, valid, two, acc);
 #pragma unroll
           for (int w = 0; w < NTW; ++w) {
-            if (w > 0 && !two) break;
-            const int tile = NTW * warp + w;
+            if (!valid || (w > 0 && !two)) break;
+            const int tile = tile0 + w;
             double2 *Tp = reinterpret_cast<double2 *>(A.T) + ((mat * mtr) * NK + tile) * 64 + pl * 32 + lane;
 #pragma unroll
             for (int i = 0; i < MT; ++i)
@@ -326,7 +335,7 @@ static cudaError_t launch_stream_t(int grid, size_t smem, const EngDev &E, const
                                    const StreamArgs &A, const StreamLayout &L, cudaStream_t st) {
   cudaError_t ce = cudaFuncSetAttribute(k_rk4_stream<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce != cudaSuccess) return ce;
-  k_rk4_stream<NK, NTW><<<grid, 32 * ((NK + NTW - 1) / NTW), smem, st>>>(E, P, h, nsteps, traj0, ntb, A, L);
+  k_rk4_stream<NK, NTW><<<grid, 32 * L.nwarp, smem, st>>>(E, P, h, nsteps, traj0, ntb, A, L);
   return cudaGetLastError();
 }
 
@@ -339,6 +348,12 @@ static cudaError_t launch_stream(int grid, const EngDev &E, const PotDev &P, dou
     SC_STREAM_CASE(5) SC_STREAM_CASE(6) SC_STREAM_CASE(7) SC_STREAM_CASE(8) SC_STREAM_CASE(9) SC_STREAM_CASE(10)
     SC_STREAM_CASE(11) SC_STREAM_CASE(12) SC_STREAM_CASE(13) SC_STREAM_CASE(14) SC_STREAM_CASE(15) SC_STREAM_CASE(16)
 #undef SC_STREAM_CASE
+    // 64 < d <= 96: one tile per warp, several CTAs (tile groups) per trajectory, each streaming the Hessians itself
+#define SC_STREAM_CASE1(N) \
+  case N: return launch_stream_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, A, L, st);
+    SC_STREAM_CASE1(17) SC_STREAM_CASE1(18) SC_STREAM_CASE1(19) SC_STREAM_CASE1(20) SC_STREAM_CASE1(21) SC_STREAM_CASE1(22)
+    SC_STREAM_CASE1(23) SC_STREAM_CASE1(24)
+#undef SC_STREAM_CASE1
     default: return cudaErrorInvalidValue;
   }
 }
@@ -426,7 +441,7 @@ static cudaError_t launch_rmult(const EngDev &E, long long nmat, const double *T
   }
   switch (L.nta) {
     SC_RMULT_CASE(1) SC_RMULT_CASE(2) SC_RMULT_CASE(3) SC_RMULT_CASE(4) SC_RMULT_CASE(5) SC_RMULT_CASE(6) SC_RMULT_CASE(7)
-    SC_RMULT_CASE(8)
+    SC_RMULT_CASE(8) SC_RMULT_CASE(9) SC_RMULT_CASE(10) SC_RMULT_CASE(11) SC_RMULT_CASE(12)
     default: return cudaErrorInvalidValue;
   }
 #undef SC_RMULT_CASE
@@ -436,7 +451,7 @@ static cudaError_t launch_rmult(const EngDev &E, long long nmat, const double *T
 // outputs per (step, tl):  qp[(step ntb + tl) 2 d ..] = q, p after the step;  aux[(step ntb + tl) 8 + 6] = S, [+ 7] = T + V of
 // the 4th stage point (propagators.py:380)
 constexpr int PATH_WARPS = 8;
-constexpr int PATH_NE = 2;                              // components per lane (d <= 64)
+constexpr int PATH_NE = (SC_MAX_DIM + 31) / 32;         // components per lane
 
 // harmonic molecule (potentials.py:581-593): grad = g0 + H0 (q - pos0), V = e0 + g0.dr + dr.H0.dr / 2 - origin.  H0 in shared
 // memory with an odd leading dimension (lane = row: conflict free)
@@ -945,8 +960,10 @@ k_corr_now(EngDev E, double *__restrict__ partials) {
 // dense_engine: separable models too (their diagonal Hessians are expanded to full matrices: the kernel multiplies
 // whatever it is given; sc_chunk.cuh is the path that knows about the structure)
 static bool stream_supported(const EngDev &E, const PotDev &P, bool dense_engine) {
-  if (E.d < 17 || E.d > 64) return false;
-  if (P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE || P.type == POT_GDML) return true;
+  if (E.d < 17 || E.d > SC_MAX_DIM) return false;
+  if (P.type == POT_HARMONIC) return true;
+  if (E.d > 64) return false;                  // Hessian expansion / sGDML kernels: d <= 64
+  if (P.type == POT_ROTATED_MORSE || P.type == POT_GDML) return true;
   return dense_engine && E.diag && E.dr == E.d && (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
 }
 

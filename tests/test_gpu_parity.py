@@ -464,7 +464,7 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
 
 
 # ------------------------------------------------------------------ general path: dense Gamma, rank deficient
-@pytest.mark.parametrize("d", [23, 40, 54, 60, 64])
+@pytest.mark.parametrize("d", [23, 40, 54, 60, 64, 72, 96])
 def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on the dense column pipeline (sc_stream.cuh):
     Hessian and left prefactor factors streamed through the shared-memory ring, k_rmult for the right factors (k-padding at
