@@ -17,7 +17,7 @@ HEADER = os.path.join(ROOT, "include", "semiclassical_b200.h")
 SC_OK, SC_ERR_INVALID, SC_ERR_CUDA, SC_ERR_UNSUPPORTED = 0, 1, 2, 3
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-split-compile", "0"]   # split-compile: the kernels of the one translation unit in parallel
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p

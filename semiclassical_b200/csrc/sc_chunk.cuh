@@ -415,8 +415,7 @@ static cudaError_t launch_wcols(int grid, const EngDev &E, const PotDev &P, doub
   switch (L.dk / 4) {
 #define SC_WCOLS_CASE(N)                                                                                              \
   case N:                                                                                                             \
-    return L.ntw == 2 ? launch_wcols_t<N, 2>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, queue, st)          \
-                      : launch_wcols_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, queue, st);
+    return launch_wcols_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, cm, hd, L, queue, st);
     SC_WCOLS_CASE(9) SC_WCOLS_CASE(10) SC_WCOLS_CASE(11) SC_WCOLS_CASE(12) SC_WCOLS_CASE(13) SC_WCOLS_CASE(14) SC_WCOLS_CASE(15)
     SC_WCOLS_CASE(16)
 #undef SC_WCOLS_CASE

@@ -1,5 +1,5 @@
 // sc_engine.cu -- C ABI (include/semiclassical_b200.h) and host-side dispatch of the sm_100a kernels.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC -split-compile 0
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -582,9 +582,7 @@ static int ensure_partials(sc_engine *e, size_t need, cudaStream_t st) {
 // pipe with the DMMA stream.)
 static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st) {
   const int d = e->dev.d, n = e->dev.n, sm = e->sm_count;
-  int wcols_tiles = 1;                                  // column tiles per warp of k_rk4_wcols (2: measured slower, 8 warps / SM)
-  if (const char *s = getenv("SC_WCOLS_TILES")) wcols_tiles = atoi(s) == 2 ? 2 : 1;
-  const WColsLayout LW = make_wcols_layout(d, wcols_tiles);
+  const WColsLayout LW = make_wcols_layout(d, 1);       // one column tile per warp (two: measured 8 % slower, 8 warps / SM)
   // time steps per pass over the state: the records are read and written once per pass, so longer passes amortise the
   // state traffic and the pipeline fill (K = 8 -> 10 -> 20: +2.3 %, +4 %); passes of a launch are balanced
   int KC = 20;
@@ -620,9 +618,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   size_t ngroups = 0;
   for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
   if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
-  long long rk4_per_sm = LW.ntw == 2 ? 2 : 3, lu_per_sm = 0;   // 0: the LU launcher's default occupancy
-  if (const char *s = getenv("SC_CHUNK_CTAS")) rk4_per_sm = atoi(s) > 0 ? atoi(s) : rk4_per_sm;
-  if (const char *s = getenv("SC_LU_CTAS")) lu_per_sm = atoi(s) > 0 ? atoi(s) : lu_per_sm;
+  const long long rk4_per_sm = 3, lu_per_sm = 0;        // CTAs per SM of k_rk4_wcols; 0: the LU launcher's default occupancy
   for (int s0 = 0; s0 < nsteps; s0 += KC) {
     const int ks = std::min(KC, nsteps - s0);
     size_t g0 = 0;
