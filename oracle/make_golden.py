@@ -254,11 +254,15 @@ def gdml_dynamics_case(name, propagators, potentials, gdml_predictor, ntraj, nt,
     _propagate(name, propagators, pot, fields, G0, G0, G0, pos, np.zeros(d), ntraj, dt, nt, en0, nkeep=nkeep)
 
 
-def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, dt, nt, en0, nx, seed=0, xspread=0.3):
+def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, dt, nt, en0, nx, seed=0, xspread=0.3,
+              kind="HK", alpha=None, beta=None):
     """wavefunction diagnostics of the reference HK propagator after nt steps: coefficients(), norm(), wavefunction(x)
     (propagators.py:657-782).  Stores q, p, S of every trajectory (not the monodromy blocks) besides the ensemble."""
     torch.manual_seed(seed)
-    pr = propagators.HermanKlukPropagator(T(Gi), T(Gt))
+    if kind == "WM":
+        pr = propagators.WaltonManolopoulosPropagator(T(Gi), T(Gt), alpha, beta)
+    else:
+        pr = propagators.HermanKlukPropagator(T(Gi), T(Gt))
     pr.initial_conditions(T(q0), T(p0), T(G0), ntraj=ntraj)
     zi, probi = pr.zi.numpy().copy(), pr.probi.numpy().copy()
     auto, ic = refrun.run_reference(pr, potential, dt, nt, en0)
@@ -268,7 +272,9 @@ def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, d
     x = qm[:, None] + xspread * rng.standard_normal((d, nx)) / np.sqrt(np.maximum(np.diag(Gt), 1e-3))[:, None]
     out = dict(fields)
     y = pr.y.numpy()
-    out.update(kind="HK", Gamma_i=Gi, Gamma_t=Gt, Gamma_0=G0, q0=q0, p0=p0, dt=dt, nt=nt, energy0_es=en0, zi=zi, probi=probi,
+    if kind == "WM":
+        out.update(alpha=float(alpha), beta=float(beta))
+    out.update(kind=kind, Gamma_i=Gi, Gamma_t=Gt, Gamma_0=G0, q0=q0, p0=p0, dt=dt, nt=nt, energy0_es=en0, zi=zi, probi=probi,
                autocorrelation=auto, ic_correlation=ic, t_final=float(pr.t),
                qpS_final=np.concatenate((y[:2 * d], y[-1:]), axis=0).copy(), c_final=pr.c.numpy().copy(),
                signs_C=pr.sign_trackers["prefactorC"]["signs"].numpy().real.copy(),
@@ -278,6 +284,24 @@ def diag_case(name, propagators, potential, fields, Gi, Gt, G0, q0, p0, ntraj, d
     np.savez_compressed(path, **out)
     print(f"{name:28s} n={ntraj:5d} nt={nt:4d} norm={out['norm']:.6f} max|psi|={np.abs(out['wavefunction']).max():.3e} "
           f"{os.path.getsize(path)/1024:.0f} KB")
+
+
+def diag_methylium_wm(name, propagators, potentials, readers, units, ntraj, nt, nx, alpha, **kw):
+    """WM diagnostics on the methylium harmonic model (d = 12, rank-deficient widths d' = 6): projection onto the non-zero
+    subspace inside the all-pairs norm"""
+    ddir = os.path.join(refrun.REFERENCE_ROOT, "tests", "DATA", "examples", "methylium_AH")
+    with open(os.path.join(ddir, "opt_freq_s0.fchk")) as f:
+        freq = readers.FormattedCheckpointFile(f)
+    with open(os.path.join(ddir, "opt_freq_s1.fchk")) as f:
+        exc = readers.FormattedCheckpointFile(f)
+    pot = potentials.MolecularHarmonicPotential(freq, exc)
+    x0, G0, en_zpt = exc.vibrational_groundstate()
+    pot.minimize(T(x0))
+    fields = dict(potential="harmonic", pos0=pot.pos0.numpy(), energy0=pot.energy0.numpy(), grad0=pot.grad0.numpy(),
+                  hess0=pot.hess0.numpy(), nac=pot.nac0.numpy(), masses=pot._masses.numpy(), origin=pot._origin)
+    dt = 0.005 / units.autime_to_fs
+    diag_case(name, propagators, pot, fields, G0, G0, G0, x0, np.zeros_like(x0), ntraj, dt, nt, en_zpt, nx, kind="WM",
+              alpha=alpha, beta=alpha, **kw)
 
 
 def diag_morse(name, propagators, potentials, model, ntraj, nt, nx, rotate_seed=None, **kw):
@@ -363,6 +387,21 @@ def main():
         model, xyz, masses = coumarin_model(units)
         gdml_dynamics_case("hk_gdml_coumarin", propagators, potentials, gdml_predictor, 40, 24, model=model, pos=xyz,
                            masses=masses, dt_fs=0.05, model_fixture="gdml_pot_coumarin", nkeep=3)
+    if want("diag_wm_as5"):
+        diag_morse("diag_wm_as5", propagators, potentials, workloads.as_5modes(0.02), 200, 20, 40, seed=5, kind="WM", alpha=500, beta=500)
+    if want("diag_wm_as5_rot"):
+        diag_morse("diag_wm_as5_rot", propagators, potentials, workloads.as_5modes(0.02), 120, 15, 33, rotate_seed=7, seed=6,
+                   kind="WM", alpha=500, beta=500)
+    if want("diag_wm_1d"):
+        nt = 30
+        times = np.linspace(0.0, (12.0 / 40) * 2.0 * np.pi, 100)
+        pot = potentials.NonHarmonicPotential()
+        fields = dict(potential="nonharmonic", eps=np.array([0.975]), b=np.array([12.0 ** -0.5]))
+        Gi = np.array([[5.0]])
+        diag_case("diag_wm_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 300,
+                  float(times[1] - times[0]), nt, 0.5, 64, seed=7, xspread=3.0, kind="WM", alpha=100.0, beta=100.0)
+    if want("diag_wm_methylium"):
+        diag_methylium_wm("diag_wm_methylium", propagators, potentials, readers, units, 90, 12, 25, 1.0e4, seed=8)
     if want("hk_gdml4"):
         gdml_dynamics_case("hk_gdml4", propagators, potentials, gdml_predictor, 200, 40)
 

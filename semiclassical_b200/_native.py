@@ -17,7 +17,11 @@ HEADER = os.path.join(ROOT, "include", "semiclassical_b200.h")
 SC_OK, SC_ERR_INVALID, SC_ERR_CUDA, SC_ERR_UNSUPPORTED = 0, 1, 2, 3
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC", "-split-compile", "0"]   # split-compile: the kernels of the one translation unit in parallel
+              "-Xcompiler", "-fPIC"]
+# development only: SC_FAST_BUILD=1 adds -split-compile 0 (51 s instead of 155 s), which changes ptxas' register allocation --
+# k_rk4_wcols then spills 360 bytes and the headline drops by 2-10 %; never used for measured builds
+if os.environ.get("SC_FAST_BUILD") == "1":
+    NVCC_FLAGS += ["-split-compile", "0"]
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _vp = ctypes.c_void_p

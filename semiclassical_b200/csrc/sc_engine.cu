@@ -1,5 +1,5 @@
 // sc_engine.cu -- C ABI (include/semiclassical_b200.h) and host-side dispatch of the sm_100a kernels.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC -split-compile 0
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -93,6 +93,9 @@ struct WMState {
   // K-step fused launches: snapshots of (step, trajectory) records, per-group rows, HK rows (energies)
   void *snap = nullptr;
   size_t snap_cap = 0;
+  // wavefunction diagnostics: trajectory-minor arrays written by the WM_DIAG pass + partial rows
+  double *diag = nullptr;
+  size_t diag_cap = 0;
 };
 
 struct sc_potential {
@@ -128,6 +131,8 @@ struct sc_engine {
   size_t corr_cap = 0;
   double *diag_scratch = nullptr, *pack_scratch = nullptr;   // wavefunction diagnostics: persistent scratch
   size_t diag_cap = 0, pack_cap = 0;
+  double *stage_in = nullptr;                                // sc_engine_set_ensemble_host: device staging of (zi, probi)
+  size_t stage_in_cap = 0;
   long long ntraj_norm = 0;
   int ens_n = 0;                  // size of the ensemble the buffers in `ens` were allocated for
   long long launches = 0;
@@ -142,8 +147,10 @@ struct sc_engine {
     if (chunk_scratch) cudaFree(chunk_scratch);
     if (stream_const) cudaFree(stream_const);
     if (wm.snap) cudaFree(wm.snap);
+    if (wm.diag) cudaFree(wm.diag);
     if (diag_scratch) cudaFree(diag_scratch);
     if (pack_scratch) cudaFree(pack_scratch);
+    if (stage_in) cudaFree(stage_in);
     for (cudaEvent_t ev : tev) cudaEventDestroy(ev);
   }
 };
@@ -283,6 +290,7 @@ static int wm_setup(WMState &w, const sc_engine_config &cfg, DevPool &pool) {
   w.dev.alpha = cfg.alpha;
   w.dev.beta = cfg.beta;
   w.dev.pref = std::sqrt(cfg.detG0) * std::pow(cfg.detGt, 0.25) * std::pow(cfg.detGi, 0.25) / std::sqrt(cfg.detGi0);
+  w.dev.pref_coef = std::pow(cfg.detG0, 0.25) * std::pow(cfg.detGt, 0.25) * std::pow(cfg.detGi, 0.25) / std::sqrt(cfg.detGi0);
   std::vector<double> GiG(dd, 0.0), Cqq(dd, 0.0);
   for (int i = 0; i < d; ++i)
     for (int j = 0; j < d; ++j) {
@@ -1068,17 +1076,19 @@ extern "C" int sc_engine_set_ensemble_host(sc_engine *e, int n, long long ntraj_
                                            const double *probi_host, void *stream) {
   if (!e || !zi_host || !probi_host) return fail(SC_ERR_INVALID, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  double *zi = nullptr, *pr = nullptr;
   const size_t nz = (size_t)2 * e->dev.d * n;
-  CU(cudaMalloc(&zi, sizeof(double) * nz));
-  CU(cudaMalloc(&pr, sizeof(double) * n));
+  if (nz + n > e->stage_in_cap) {                        // staging buffer kept for the next repetition
+    CU(cudaStreamSynchronize(st));
+    if (e->stage_in) cudaFree(e->stage_in);
+    e->stage_in = nullptr;
+    e->stage_in_cap = 0;
+    CU(cudaMalloc(&e->stage_in, sizeof(double) * (nz + n)));
+    e->stage_in_cap = nz + n;
+  }
+  double *zi = e->stage_in, *pr = zi + nz;
   CU(cudaMemcpyAsync(zi, zi_host, sizeof(double) * nz, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(pr, probi_host, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  int rc = sc_engine_set_ensemble(e, n, ntraj_norm, zi, pr, stream);
-  cudaStreamSynchronize(st);
-  cudaFree(zi);
-  cudaFree(pr);
-  return rc;
+  return sc_engine_set_ensemble(e, n, ntraj_norm, zi, pr, stream);
 }
 
 static int check_step_args(sc_engine *e, const sc_potential *pot) {
@@ -1224,6 +1234,11 @@ extern "C" int sc_engine_set_state(sc_engine *e, const double *y, void *stream) 
   return SC_OK;
 }
 
+__global__ void k_fill(double *x, size_t n, double v) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) x[i] = v;
+}
+
 extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, double *signs, void *stream) {
   if (!e || e->dev.n < 1) return fail(SC_ERR_INVALID, "no ensemble");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1236,9 +1251,8 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
       CU(cudaMemcpyAsync(signs + n, e->wm.dev.signA, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
       CU(cudaMemcpyAsync(signs + 2 * n, e->wm.dev.signM, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     } else {
-      std::vector<double> ones(2 * (size_t)n, 1.0);
-      CU(cudaMemcpyAsync(signs + n, ones.data(), sizeof(double) * 2 * n, cudaMemcpyHostToDevice, st));
-      CU(cudaStreamSynchronize(st));
+      k_fill<<<(2 * n + 255) / 256, 256, 0, st>>>(signs + n, 2 * (size_t)n, 1.0);   // no "detA" / "detM" trackers: +1
+      CU(cudaGetLastError());
     }
   }
   return SC_OK;
@@ -1246,17 +1260,6 @@ extern "C" int sc_engine_get_prefactor(sc_engine *e, double *c, double *c2, doub
 
 // ------------------------------------------------------------------ wavefunction diagnostics (sc_gauss.cuh) ---------
 namespace {
-struct DevBufs {                      // scratch of one diagnostic call
-  std::vector<void *> p;
-  ~DevBufs() { for (void *q : p) cudaFree(q); }
-  template <class T> cudaError_t get(T **out, size_t count) {
-    void *q = nullptr;
-    cudaError_t ce = cudaMalloc(&q, sizeof(T) * (count ? count : 1));
-    if (ce == cudaSuccess) p.push_back(q);
-    *out = static_cast<T *>(q);
-    return ce;
-  }
-};
 cudaError_t launch_gauss_sum(int n_bra, int n_ket, int kp, const double *a, const double *alpha, const double *gamma,
                              const double *r, const double *s, const double *alphaJ, const double *beta, const double2 *coef,
                              double2 *out, cudaStream_t st) {
@@ -1268,14 +1271,79 @@ cudaError_t launch_gauss_sum(int n_bra, int n_ket, int kp, const double *a, cons
 }
 }  // namespace
 
-// expansion coefficients v_i of the frozen-Gaussian wavefunction (HermanKlukPropagator.coefficients, propagators.py:657-686)
+// Walton-Manolopoulos diagnostics (propagators.py:1391-1575): one WM_DIAG pass of k_wm rebuilds CQQ, CqQ, PI_Q, det A of the
+// current state and leaves the coefficients v_n (eqn 75) and the per-trajectory matrices of the wavefunction / norm kernels in
+// trajectory-minor arrays
+static int wm_diag_pass(sc_engine *e, cudaStream_t st, double **partials_out) {
+  WMState &w = e->wm;
+  const int n = e->dev.n, d = e->dev.d, dr = e->dev.dr;
+  if (d > WMD_MAX) return fail(SC_ERR_UNSUPPORTED, "Walton-Manolopoulos diagnostics: d = %d > %d", d, WMD_MAX);
+  const size_t per = 2 * (1 + (size_t)d * d + (size_t)dr * d + (size_t)dr * dr + d + dr) + d;      // doubles per trajectory
+  const size_t need = per * n + 2 * (size_t)e->sm_count * 8 + 16;
+  if (need > w.diag_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (w.diag) cudaFree(w.diag);
+    w.diag = nullptr;
+    w.diag_cap = 0;
+    CU(cudaMalloc(&w.diag, sizeof(double) * need));
+    w.diag_cap = need;
+  }
+  double2 *b2 = reinterpret_cast<double2 *>(w.diag);
+  w.dev.dg_v = b2;                  b2 += n;
+  w.dev.dg_CQQ = b2;                b2 += (size_t)d * d * n;
+  w.dev.dg_UC = b2;                 b2 += (size_t)dr * d * n;
+  w.dev.dg_CP = b2;                 b2 += (size_t)dr * dr * n;
+  w.dev.dg_D = b2;                  b2 += (size_t)d * n;
+  w.dev.dg_DP = b2;                 b2 += (size_t)dr * n;
+  w.dev.dg_Q = reinterpret_cast<double *>(b2);
+  if (partials_out) *partials_out = w.dev.dg_Q + (size_t)d * n;
+  w.dev.diag_inv_norm = 1.0 / (double)e->ntraj_norm;
+  const int threads = w.tpt * w.groups;
+  if (w.tpt == 32) {
+    CU(cudaFuncSetAttribute(k_wm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<32><<<w.grid, threads, w.smem, st>>>(e->dev, w.dev, w.L, WM_DIAG, w.partials);
+  } else {
+    CU(cudaFuncSetAttribute(k_wm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<128><<<w.grid, threads, w.smem, st>>>(e->dev, w.dev, w.L, WM_DIAG, w.partials);
+  }
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return SC_OK;
+}
+
+// expansion coefficients v_i of the frozen-Gaussian wavefunction (HermanKlukPropagator.coefficients, propagators.py:657-686;
+// WaltonManolopoulosPropagator.coefficients, propagators.py:1391-1432)
 extern "C" int sc_engine_coefficients(sc_engine *e, double *v_dev, void *stream) {
   if (!e || e->dev.n < 1 || !v_dev) return fail(SC_ERR_INVALID, "no ensemble");
-  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "coefficients(): Herman-Kluk propagator only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (e->cfg.wm) {
+    if (int rc = wm_diag_pass(e, st, nullptr)) return rc;
+    CU(cudaMemcpyAsync(v_dev, e->wm.dev.dg_v, sizeof(double2) * e->dev.n, cudaMemcpyDeviceToDevice, st));
+    return SC_OK;
+  }
   const int n = e->dev.n;
   k_coefficients<<<(n + 255) / 256, 256, 0, st>>>(e->dev, 1.0 / (double)e->ntraj_norm, reinterpret_cast<double2 *>(v_dev));
   CU(cudaGetLastError());
+  return SC_OK;
+}
+
+// WaltonManolopoulosPropagator.norm (propagators.py:1484-1575): all pairs, a (d' x d') complex inverse + determinant per pair
+static int wm_norm(sc_engine *e, double *norm2_host, cudaStream_t st) {
+  double *partials = nullptr;
+  if (int rc = wm_diag_pass(e, st, &partials)) return rc;
+  const int n = e->dev.n;
+  int grid = std::min(n, e->sm_count * 8);
+  k_wm_norm<<<grid, 128, 0, st>>>(e->dev.d, e->dev.dr, n, e->wm.dev, partials);
+  CU(cudaGetLastError());
+  double *res = partials + 2 * (size_t)grid;
+  k_wm_norm_reduce<<<1, 64, 0, st>>>(partials, grid, res);
+  CU(cudaGetLastError());
+  double h[2];
+  CU(cudaMemcpyAsync(h, res, sizeof(h), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  norm2_host[0] = h[0];
+  norm2_host[1] = h[1];
+  e->launches += 2;
   return SC_OK;
 }
 
@@ -1310,7 +1378,7 @@ extern "C" int sc_engine_norm_pack(sc_engine *e, const double *A_host, const dou
                                    double *pack_dev, void *stream) {
   if (!e || e->dev.n < 1 || !A_host || !B_host || !C_host || !pack_dev || n_pad < e->dev.n)
     return fail(SC_ERR_INVALID, "norm_pack(): bad arguments");
-  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "norm(): Herman-Kluk propagator only");
+  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "sharded norm(): Herman-Kluk propagator only");
   if (gs_smem_bytes((2 * e->dev.d + 3) & ~3) > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "norm(): d = %d exceeds the all-pairs kernel's tiles (d <= 64)", e->dev.d);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int n = e->dev.n, d = e->dev.d, kp = (2 * d + 3) & ~3;
@@ -1366,6 +1434,7 @@ extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *
                               double *norm2_host, void *stream) {
   if (!e || e->dev.n < 1 || !norm2_host) return fail(SC_ERR_INVALID, "norm(): bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (e->cfg.wm) return wm_norm(e, norm2_host, st);           // A, B, C, fac are Herman-Kluk quantities: unused
   const int n = e->dev.n, kp = (2 * e->dev.d + 3) & ~3;
   const size_t packsz = (size_t)n * (2 * kp + 4);
   if (packsz > e->pack_cap) {
@@ -1387,16 +1456,33 @@ extern "C" int sc_engine_norm(sc_engine *e, const double *A_host, const double *
 extern "C" int sc_engine_wavefunction(sc_engine *e, const double *Gt_host, double fac, int nx, const double *x_dev,
                                       double *phi_dev, void *stream) {
   if (!e || e->dev.n < 1 || !Gt_host || !x_dev || !phi_dev || nx < 1) return fail(SC_ERR_INVALID, "wavefunction(): bad arguments");
-  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "wavefunction(): Herman-Kluk propagator only");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (e->cfg.wm) {
+    // eqn (75), propagators.py:1434-1482 (Gt_host, fac are Herman-Kluk quantities: unused)
+    if (int rc = wm_diag_pass(e, st, nullptr)) return rc;
+    k_wm_wavefunction<<<std::min(nx, e->sm_count * 8), 256, 0, st>>>(e->dev.d, e->dev.n, nx, x_dev, e->wm.dev,
+                                                                     reinterpret_cast<double2 *>(phi_dev));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));
+    e->launches += 1;
+    return SC_OK;
+  }
   const int n = e->dev.n, d = e->dev.d, kp = (d + 3) & ~3;
-  DevBufs B;
-  double *G, *a, *r, *s, *alpha, *gamma, *alphaJ, *beta;
-  double2 *v;
-  CU(B.get(&G, (size_t)d * d));
-  CU(B.get(&a, (size_t)nx * kp)); CU(B.get(&alpha, nx)); CU(B.get(&gamma, nx));
-  CU(B.get(&r, (size_t)n * kp)); CU(B.get(&s, (size_t)n * kp)); CU(B.get(&alphaJ, n)); CU(B.get(&beta, n));
-  CU(B.get(&v, n));
+  if (gs_smem_bytes(kp) > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "wavefunction(): d = %d exceeds the kernel's tiles", d);
+  // persistent scratch (pack_scratch): G | a (nx kp) | alpha, gamma (nx) | r, s (n kp) | alphaJ, beta (n) | v (2 n)
+  const size_t g2 = ((size_t)d * d + 1) & ~(size_t)1;
+  const size_t need = g2 + (size_t)nx * (kp + 2) + (size_t)n * (2 * kp + 4) + 8;
+  if (need > e->pack_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->pack_scratch) cudaFree(e->pack_scratch);
+    e->pack_scratch = nullptr;
+    e->pack_cap = 0;
+    CU(cudaMalloc(&e->pack_scratch, sizeof(double) * need));
+    e->pack_cap = need;
+  }
+  double *G = e->pack_scratch, *a = G + g2, *alpha = a + (size_t)nx * kp, *gamma = alpha + nx;
+  double *r = gamma + nx, *s = r + (size_t)n * kp, *alphaJ = s + (size_t)n * kp, *beta = alphaJ + n;
+  double2 *v = reinterpret_cast<double2 *>(beta + n);
   CU(cudaMemcpyAsync(G, Gt_host, sizeof(double) * d * d, cudaMemcpyHostToDevice, st));
   k_coefficients<<<(n + 255) / 256, 256, 0, st>>>(e->dev, fac / (double)e->ntraj_norm, v);
   CU(cudaGetLastError());

@@ -86,7 +86,11 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   __shared__ int cnt[MAXS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int d = E.d, dp = (d + 1) & ~1, dr = E.dr;
-  const int NS = L.ns, hsz = L.hsz, nwarps = (int)(blockDim.x >> 5), ngroups = L.ngroups;
+  // NK <= 16: one CTA holds all tiles of a trajectory (compile-time warp count, no ragged groups); above: tile groups
+  constexpr bool GROUPS = NK > 16;
+  constexpr int NWARP = (NK + NTW - 1) / NTW;
+  const int NS = L.ns, hsz = L.hsz;
+  const int nwarps = GROUPS ? (int)(blockDim.x >> 5) : NWARP, ngroups = GROUPS ? L.ngroups : 1;
   const bool dense = A.T != nullptr;
   const int nrk = A.skip_rk4 ? 0 : 4;
   const int nstg = nrk + (dense ? 2 : 0);
@@ -128,7 +132,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
     if (g >= G) return;
     const int it = (int)(g / per_traj_d), rem = (int)(g - (long long)it * per_traj_d);
     const int step = rem / nstg, sidx = rem - step * nstg + (4 - nrk);
-    const int tl = (int)(((long long)blockIdx.x + (long long)it * gridDim.x) / ngroups);
+    const int tl = GROUPS ? (int)(((long long)blockIdx.x + (long long)it * gridDim.x) / ngroups) : (int)blockIdx.x + it * (int)gridDim.x;
     const double *src;
     if (sidx < 4) src = A.hs_const ? A.hs : A.hs + ((size_t)(step * 4 + sidx) * ntb + tl) * hsz;
     else src = (sidx == 4) ? A.L1p : A.L2p;
@@ -184,11 +188,17 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   };
 
   for (int it = 0; it < n_iter; ++it) {
-    const long long item = (long long)blockIdx.x + (long long)it * gridDim.x;
-    const int tl = (int)(item / ngroups), grp = (int)(item - (long long)tl * ngroups);
+    int tl, grp = 0;
+    if (GROUPS) {
+      const long long item = (long long)blockIdx.x + (long long)it * gridDim.x;
+      tl = (int)(item / ngroups);
+      grp = (int)(item - (long long)tl * ngroups);
+    } else {
+      tl = (int)blockIdx.x + it * (int)gridDim.x;
+    }
     const int traj = traj0 + tl;
     const int tile0 = (grp * nwarps + warp) * NTW;          // first column tile of this warp
-    const bool valid = tile0 < NK;                          // warp-uniform: the last group of a trajectory may be ragged
+    const bool valid = GROUPS ? tile0 < NK : true;          // warp-uniform: the last group of a trajectory may be ragged
     int b[NTW];
     bool bok[NTW];
 #pragma unroll

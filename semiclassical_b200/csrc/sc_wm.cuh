@@ -25,7 +25,7 @@
 
 namespace sc {
 
-enum WMMode { WM_STEP = 0, WM_INIT = 1, WM_CORR = 2 };
+enum WMMode { WM_STEP = 0, WM_INIT = 1, WM_CORR = 2, WM_DIAG = 3 };   // DIAG: pieces of the wavefunction diagnostics only
 
 struct WMDev {
   int d, dr;
@@ -40,6 +40,13 @@ struct WMDev {
   double2 *prevA, *prevM;                   // branch trackers "detA", "detM" (n)
   double *signA, *signM;
   const double *winv;                       // 1 / (probi (2 pi)^d)
+  // wavefunction diagnostics (coefficients / wavefunction / norm, propagators.py:1391-1575): trajectory-minor arrays
+  // [component][trajectory] written in mode WM_DIAG
+  double pref_coef, diag_inv_norm;          // detG0^(1/4) detGt^(1/4) detGi^(1/4) / sqrt(detGi0);  1 / ntraj
+  double2 *dg_v;                            // (n) coefficients, eqn (75)
+  double2 *dg_CQQ, *dg_UC, *dg_CP;          // CQQ (d^2), U^T CQQ (dr d), U^T CQQ U (dr^2)
+  double2 *dg_D, *dg_DP;                    // dvec = CqQ^T (q0 - q) + i PIQ (d), U^T dvec (dr)
+  double *dg_Q;                             // current positions (d)
 };
 
 // shared-memory workspace of one group, offsets in double2 units
@@ -360,6 +367,76 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     v2c[i] = make_double2(PIQ[i].x - SC_LDG(W.p0 + i), PIQ[i].y);      // PIQ - p0
   }
   gsync<TPT>(gid);
+  if (mode == WM_DIAG) {
+    // pieces of coefficients() / wavefunction() / norm() (propagators.py:1391-1575): nothing of the trackers is touched
+    const int n = E.n;
+    for (int idx = t; idx < dr * d; idx += TPT) {                 // UC = U^T CQQ
+      const int a = idx / d, j = idx % d;
+      double2 sum = make_double2(0.0, 0.0);
+      for (int i = 0; i < d; ++i) {
+        const double u = SC_LDG(W.U + i * dr + a);
+        sum.x += u * CQQ[i * d + j].x;
+        sum.y += u * CQQ[i * d + j].y;
+      }
+      T1[idx] = sum;
+    }
+    for (int i = t; i < d; i += TPT) {                            // dvec = CqQ^T (q0 - q) + i PIQ   (propagators.py:1511)
+      double2 sum = make_double2(-PIQ[i].y, PIQ[i].x);
+      for (int b = 0; b < d; ++b) {
+        sum.x += CqQ[b * d + i].x * dq[b];
+        sum.y += CqQ[b * d + i].y * dq[b];
+      }
+      u1[i] = sum;
+    }
+    gsync<TPT>(gid);
+    for (int idx = t; idx < dr * dr; idx += TPT) {                // CP = U^T CQQ U
+      const int a = idx / dr, b = idx % dr;
+      double2 sum = make_double2(0.0, 0.0);
+      for (int j = 0; j < d; ++j) {
+        const double u = SC_LDG(W.U + j * dr + b);
+        sum.x += T1[a * d + j].x * u;
+        sum.y += T1[a * d + j].y * u;
+      }
+      W.dg_CP[(size_t)idx * n + traj] = sum;
+    }
+    for (int a = t; a < dr; a += TPT) {
+      double2 sum = make_double2(0.0, 0.0);
+      for (int i = 0; i < d; ++i) {
+        const double u = SC_LDG(W.U + i * dr + a);
+        sum.x += u * u1[i].x;
+        sum.y += u * u1[i].y;
+      }
+      W.dg_DP[(size_t)a * n + traj] = sum;
+    }
+    for (int idx = t; idx < d2; idx += TPT) W.dg_CQQ[(size_t)idx * n + traj] = CQQ[idx];
+    for (int idx = t; idx < dr * d; idx += TPT) W.dg_UC[(size_t)idx * n + traj] = T1[idx];
+    for (int i = t; i < d; i += TPT) {
+      W.dg_D[(size_t)i * n + traj] = u1[i];
+      W.dg_Q[(size_t)i * n + traj] = Qv[i];
+    }
+    if (t == 0) {
+      // eqn (75) as coded in coefficients(), propagators.py:1407-1430; eps of eqn (74) with b0 = 0
+      double viv = 0.0, qCq = 0.0, piq = 0.0;
+      for (int i = 0; i < d; ++i) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < d; ++k) {
+          s1 += SC_LDG(W.iGi0 + i * d + k) * v2[k];
+          s2 += SC_LDG(W.Cqq + i * d + k) * dq[k];
+        }
+        viv += v2[i] * s1;
+        qCq += dq[i] * s2;
+        piq += PIq[i] * dq[i];
+      }
+      const double2 c = E.c[traj];
+      const double s0 = E.sign[traj] * W.signA[traj] * W.pref_coef * W.winv[traj] * W.diag_inv_norm;
+      double2 v = c_mul(make_double2(s0 * c.x, s0 * c.y), make_double2(cos(S), sin(S)));
+      v = c_mul(v, c_inv(c_sqrt(detA)));
+      v = c_mul(v, c_exp(make_double2(-0.5 * viv - 0.5 * qCq, -piq)));
+      W.dg_v[traj] = v;
+    }
+    gsync<TPT>(gid);
+    return;
+  }
   // eqn (78): M = Gamma_0 + CQQ, projected: M' = U^T M U
   for (int idx = t; idx < dr * d; idx += TPT) {
     const int a = idx / d, j = idx % d;
@@ -597,6 +674,166 @@ __global__ void k_wm_reduce_k(const double *partials, int ngroups, int nsteps, d
   } else if (j == 4 && lane == 0) {
     out[k * 5 + 4] = energy_rows[k * 5 + 4];
   }
+}
+
+// ------------------------------------------------------------------ WM wavefunction diagnostics
+constexpr int WMD_MAX = 16;      // largest d of the diagnostic kernels (per-thread local matrices)
+
+// psi(x_k) = sum_n v_n exp(-1/2 y CQQ_n y + dvec_n . y), y = x_k - Q_n   (propagators.py:1434-1482); one CTA per grid point
+__global__ void __launch_bounds__(256)
+k_wm_wavefunction(int d, int n, int nx, const double *__restrict__ x, WMDev W, double2 *__restrict__ phi) {
+  __shared__ double red[2][8];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  for (int k = blockIdx.x; k < nx; k += gridDim.x) {
+    double sx = 0.0, sy = 0.0;
+    for (int traj = t; traj < n; traj += 256) {
+      double y[WMD_MAX];
+      for (int a = 0; a < d; ++a) y[a] = x[(size_t)a * nx + k] - W.dg_Q[(size_t)a * n + traj];
+      double2 ex = make_double2(0.0, 0.0);
+      for (int a = 0; a < d; ++a) {
+        double2 r = W.dg_D[(size_t)a * n + traj];
+        for (int b = 0; b < d; ++b) {
+          const double2 c = W.dg_CQQ[(size_t)(a * d + b) * n + traj];
+          r.x -= 0.5 * c.x * y[b];
+          r.y -= 0.5 * c.y * y[b];
+        }
+        ex.x += y[a] * r.x;
+        ex.y += y[a] * r.y;
+      }
+      const double2 term = c_mul(W.dg_v[traj], c_exp(ex));
+      sx += term.x;
+      sy += term.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    __syncthreads();
+    if (lane == 0) { red[0][w] = sx; red[1][w] = sy; }
+    __syncthreads();
+    if (t == 0) {
+      double ax = 0.0, ay = 0.0;
+      for (int i = 0; i < 8; ++i) { ax += red[0][i]; ay += red[1][i]; }
+      phi[k] = make_double2(ax, ay);
+    }
+  }
+}
+
+// |psi|^2 = sum_ij conj(v_i) O_ij v_j with the "overlap" of propagators.py:1520-1565: D = conj(CQQ_i) + CQQ_j in the non-zero
+// subspace (dr x dr), its inverse applied to b = CQQ_j dQ + conj(d_i) + d_j and its determinant by Gaussian elimination with
+// partial pivoting in per-thread local memory.  One CTA per bra i, threads over the kets j (trajectory-minor arrays: coalesced);
+// partial sums (gridDim.x, 2), one writer per row.
+__global__ void __launch_bounds__(128)
+k_wm_norm(int d, int dr, int n, WMDev W, double *__restrict__ partials) {
+  __shared__ double2 sCP[WMD_MAX * WMD_MAX], sDP[WMD_MAX];
+  __shared__ double sQ[WMD_MAX], red[2][4];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  double accx = 0.0, accy = 0.0;
+  const double inv2pi = 1.0 / (2.0 * M_PI);
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    __syncthreads();
+    for (int idx = t; idx < dr * dr; idx += 128) sCP[idx] = W.dg_CP[(size_t)idx * n + i];
+    if (t < dr) sDP[t] = W.dg_DP[(size_t)t * n + i];
+    if (t < d) sQ[t] = W.dg_Q[(size_t)t * n + i];
+    __syncthreads();
+    const double2 vi = W.dg_v[i];
+    for (int j = t; j < n; j += 128) {
+      double dQ[WMD_MAX];
+      for (int a = 0; a < d; ++a) dQ[a] = W.dg_Q[(size_t)a * n + j] - sQ[a];
+      // -1/2 dQ CQQ_j dQ - d_j . dQ
+      double2 ex = make_double2(0.0, 0.0);
+      for (int a = 0; a < d; ++a) {
+        double2 r = W.dg_D[(size_t)a * n + j];
+        r.x = -r.x; r.y = -r.y;
+        for (int b = 0; b < d; ++b) {
+          const double2 c = W.dg_CQQ[(size_t)(a * d + b) * n + j];
+          r.x -= 0.5 * c.x * dQ[b];
+          r.y -= 0.5 * c.y * dQ[b];
+        }
+        ex.x += dQ[a] * r.x;
+        ex.y += dQ[a] * r.y;
+      }
+      // b' = U^T (CQQ_j dQ + conj(d_i) + d_j),  D' = conj(CP_i) + CP_j
+      double2 D[WMD_MAX * WMD_MAX], bp[WMD_MAX], z[WMD_MAX];
+      for (int a = 0; a < dr; ++a) {
+        double2 r = W.dg_DP[(size_t)a * n + j];
+        r.x += sDP[a].x;
+        r.y -= sDP[a].y;
+        for (int b = 0; b < d; ++b) {
+          const double2 c = W.dg_UC[(size_t)(a * d + b) * n + j];
+          r.x += c.x * dQ[b];
+          r.y += c.y * dQ[b];
+        }
+        bp[a] = r;
+        z[a] = r;
+        for (int b = 0; b < dr; ++b) {
+          const double2 c = W.dg_CP[(size_t)(a * dr + b) * n + j];
+          D[a * dr + b] = make_double2(sCP[a * dr + b].x + c.x, -sCP[a * dr + b].y + c.y);
+        }
+      }
+      // Gaussian elimination with partial pivoting: det(D' / (2 pi)), z = D'^-1 b'
+      double2 det = make_double2(1.0, 0.0);
+      for (int k = 0; k < dr; ++k) {
+        int p = k;
+        double best = D[k * dr + k].x * D[k * dr + k].x + D[k * dr + k].y * D[k * dr + k].y;
+        for (int r = k + 1; r < dr; ++r) {
+          const double m = D[r * dr + k].x * D[r * dr + k].x + D[r * dr + k].y * D[r * dr + k].y;
+          if (m > best) { best = m; p = r; }
+        }
+        if (p != k) {
+          for (int c = k; c < dr; ++c) { const double2 tmp = D[k * dr + c]; D[k * dr + c] = D[p * dr + c]; D[p * dr + c] = tmp; }
+          const double2 tmp = z[k]; z[k] = z[p]; z[p] = tmp;
+          det.x = -det.x; det.y = -det.y;
+        }
+        const double2 piv = D[k * dr + k];
+        det = c_mul(det, make_double2(piv.x * inv2pi, piv.y * inv2pi));
+        const double2 ip = c_inv(piv);
+        for (int r = k + 1; r < dr; ++r) {
+          const double2 f = c_mul(D[r * dr + k], ip);
+          for (int c = k + 1; c < dr; ++c) {
+            const double2 u = D[k * dr + c];
+            D[r * dr + c].x -= f.x * u.x - f.y * u.y;
+            D[r * dr + c].y -= f.x * u.y + f.y * u.x;
+          }
+          z[r].x -= f.x * z[k].x - f.y * z[k].y;
+          z[r].y -= f.x * z[k].y + f.y * z[k].x;
+        }
+      }
+      for (int k = dr - 1; k >= 0; --k) {
+        double2 r = z[k];
+        for (int c = k + 1; c < dr; ++c) {
+          const double2 u = D[k * dr + c];
+          r.x -= u.x * z[c].x - u.y * z[c].y;
+          r.y -= u.x * z[c].y + u.y * z[c].x;
+        }
+        z[k] = c_mul(r, c_inv(D[k * dr + k]));
+      }
+      for (int a = 0; a < dr; ++a) {                           // + 1/2 b'^T D'^-1 b'
+        ex.x += 0.5 * (bp[a].x * z[a].x - bp[a].y * z[a].y);
+        ex.y += 0.5 * (bp[a].x * z[a].y + bp[a].y * z[a].x);
+      }
+      double2 ol = c_mul(c_inv(c_sqrt(det)), c_exp(ex));
+      ol = c_mul(ol, W.dg_v[j]);
+      accx += vi.x * ol.x + vi.y * ol.y;                       // conj(v_i) * ...
+      accy += vi.x * ol.y - vi.y * ol.x;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { accx += __shfl_xor_sync(0xffffffffu, accx, o); accy += __shfl_xor_sync(0xffffffffu, accy, o); }
+  if (lane == 0) { red[0][w] = accx; red[1][w] = accy; }
+  __syncthreads();
+  if (t == 0) {
+    partials[(size_t)blockIdx.x * 2] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    partials[(size_t)blockIdx.x * 2 + 1] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+  }
+}
+
+__global__ void k_wm_norm_reduce(const double *partials, int nrows, double *out2) {
+  const int j = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (j >= 2) return;
+  double s = 0.0;
+  for (int g = lane; g < nrows; g += 32) s += partials[(size_t)g * 2 + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out2[j] = s;
 }
 
 // deterministic second pass: out[0..3] = inv_norm * sum over groups; out[4] = energy passthrough

@@ -358,9 +358,12 @@ def test_chunked_path_against_oracle(d, cuda_device):
 
 
 # ------------------------------------------------------------------ wavefunction diagnostics (propagators.py:657-782)
-@pytest.mark.parametrize("name", ["diag_as5", "diag_as5_rot", "diag_as24", "diag_1d"])
+@pytest.mark.parametrize("name", ["diag_as5", "diag_as5_rot", "diag_as24", "diag_1d", "diag_wm_as5", "diag_wm_as5_rot", "diag_wm_1d",
+                                  "diag_wm_methylium"])
 def test_wavefunction_diagnostics_match_reference(name, cuda_device):
-    """coefficients(), norm() (all-pairs DMMA kernel), wavefunction(x) after nt steps vs the reference's own values"""
+    """coefficients(), norm() (all-pairs DMMA kernel), wavefunction(x) after nt steps vs the reference's own values; the
+    diag_wm_* fixtures are the Walton-Manolopoulos versions (propagators.py:1391-1575: eqn (75) coefficients, per-pair
+    (d' x d') complex inverse + determinant in the norm; methylium: rank-deficient widths, d' = 6 of d = 12)"""
     g = helpers.load_golden(name)
     pot = helpers.potential_from_golden(g)
     pr = helpers.propagator_from_golden(g, cuda_device)
