@@ -16,6 +16,7 @@
 #include "sc_mma.cuh"
 #include "sc_chunk.cuh"
 #include "sc_stream.cuh"
+#include "sc_gdml2.cuh"
 #include "sc_lu_batch.cuh"
 #include "sc_potentials.cuh"
 #include "sc_wm.cuh"

@@ -17,6 +17,7 @@
 // the reference's own result moves by ~3e-9 (absolute) under a permutation of the training set.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 #include "sc_device.cuh"
 
@@ -298,9 +299,14 @@ k_gdml_eval(PotDev P, int n, const double *__restrict__ r, double *__restrict__ 
 }
 
 // returns 0 on launch, 1 if the configuration is outside the kernel's envelope
+static int launch_gdml_eval2(const PotDev &P, int n, const double *r, double *V, double *grad, double *hess, cudaStream_t st,
+                             int hs_ld, size_t hs_stride);   // sc_gdml2.cuh
+
 static int launch_gdml_eval(const PotDev &P, int n, const double *r, double *V, double *grad, double *hess, cudaStream_t st,
                             int hs_ld = 0, size_t hs_stride = 0) {
   const int N = P.n_atoms, D = P.n_desc;
+  // second-generation kernel (register-resident Jacobian, DMMA rank-M update) inside its envelope, unless SC_GDML_V1=1
+  if (!getenv("SC_GDML_V1") && launch_gdml_eval2(P, n, r, V, grad, hess, st, hs_ld, hs_stride) == 0) return 0;
   if (N * (N + 1) / 2 > GDML_THREADS) return 1;
   const GdmlLayout L = make_gdml_layout(N, D);
   const size_t smem = sizeof(double) * (size_t)L.total;

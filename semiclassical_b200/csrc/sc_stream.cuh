@@ -147,7 +147,8 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
 
   long long g = 0;
   // wait for stage g, acc = A_g B (B: this warp's U or V slabs), release the slot
-  auto mma_stage = [&](const double *__restrict__ Bb, bool valid, bool two, double (&acc)[NTW][MT][2]) {
+  // mt_lim: row tiles beyond it are all padding (left prefactor factors with d' <= 8 (MT - 1)): skipped, warp-uniform
+  auto mma_stage = [&](const double *__restrict__ Bb, bool valid, bool two, double (&acc)[NTW][MT][2], int mt_lim) {
     const int slot = (int)(g % NS);
     mbar_wait(&full[slot], (uint32_t)((g / NS) & 1));
     if (valid) {
@@ -165,12 +166,14 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       double af[MT];
 #pragma unroll
       for (int i = 0; i < MT - 1; ++i) af[i] = Hfr0[i * 8 * LDH + 4 * kk];
-      af[MT - 1] = last_ok ? Hfrl[(MT - 1) * 8 * LDH + 4 * kk] : 0.0;
+      af[MT - 1] = (last_ok && MT - 1 < mt_lim) ? Hfrl[(MT - 1) * 8 * LDH + 4 * kk] : 0.0;
 #pragma unroll
-      for (int i = 0; i < MT; ++i) dmma884(acc[0][i][0], acc[0][i][1], af[i], bf[0]);
+      for (int i = 0; i < MT - 1; ++i) dmma884(acc[0][i][0], acc[0][i][1], af[i], bf[0]);
+      if (MT - 1 < mt_lim) dmma884(acc[0][MT - 1][0], acc[0][MT - 1][1], af[MT - 1], bf[0]);
       if (NTW > 1 && two) {
 #pragma unroll
-        for (int i = 0; i < MT; ++i) dmma884(acc[NTW - 1][i][0], acc[NTW - 1][i][1], af[i], bf[NTW - 1]);
+        for (int i = 0; i < MT - 1; ++i) dmma884(acc[NTW - 1][i][0], acc[NTW - 1][i][1], af[i], bf[NTW - 1]);
+        if (MT - 1 < mt_lim) dmma884(acc[NTW - 1][MT - 1][0], acc[NTW - 1][MT - 1][1], af[MT - 1], bf[NTW - 1]);
       }
     }
     }
@@ -240,7 +243,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
       const size_t mat = (size_t)step * ntb + tl;
 #pragma unroll 1
       for (int s = 1; s <= nrk; ++s) {
-        mma_stage(Ub, valid, two, acc);
+        mma_stage(Ub, valid, two, acc, MT);
         // ---- RK4 bookkeeping on the warp's own slabs, stage operand in place
 #pragma unroll
         for (int w = 0; w < NTW; ++w) {
@@ -305,7 +308,7 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
         const int mtr = L.mtr;
 #pragma unroll 1
         for (int pl = 0; pl < 2; ++pl) {
-          mma_stage(Ub + pl * SLAB, valid, two, acc);
+          mma_stage(Ub + pl * SLAB, valid, two, acc, mtr);
 #pragma unroll
           for (int w = 0; w < NTW; ++w) {
             if (!valid || (w > 0 && !two)) break;
