@@ -1150,7 +1150,11 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
       e->dev.snap_sign = nullptr;
       if (rc) return rc;
       CU(cudaMemsetAsync(wpart, 0, sizeof(double) * ngr * ks * 4, st));
-      if (w.tpt == 32) {
+      if (w.tpt == 32 && e->dev.d == 5 && e->dev.dr == 5 && !getenv("SC_WM_RUNTIME_D")) {
+        // BASELINE configs[1]: 5 modes, full-rank widths -- dimension folded at compile time
+        CU(cudaFuncSetAttribute(k_wm_fused<32, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+        k_wm_fused<32, 5><<<w.grid, threads, w.smem, st>>>(Dsnap, w.dev, w.L, ks, wpart);
+      } else if (w.tpt == 32) {
         CU(cudaFuncSetAttribute(k_wm_fused<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
         k_wm_fused<32><<<w.grid, threads, w.smem, st>>>(Dsnap, w.dev, w.L, ks, wpart);
       } else {

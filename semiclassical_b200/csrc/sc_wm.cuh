@@ -178,10 +178,13 @@ SC_HD double wm_track(double sign, double2 zprev, double2 z) {
 
 // All WM work of one trajectory.  acc4 (thread 0 of the group only): running sums of the contributions to
 // C_auto (re, im) and k_ic (re, im), weights 1/(probi (2 pi)^d) applied, 1/N not applied.
-template <int TPT>
+// DC > 0: d = dr = DC at compile time (full-rank widths): the index arithmetic (idx / D2, idx % R2, ...) and the loop bounds of the
+// ~30 small matrix products fold into constants -- the runtime-d kernel spends most of its issue slots on them (14.9 k warp
+// instructions per trajectory-step at d = 5, profiles/ncu_r02_k_wm_fused.txt)
+template <int TPT, int DC = 0>
 SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, double2 *ws, int traj, int mode, int t,
                          int gid, double *acc4) {
-  const int d = W.d, dr = W.dr, D2 = 2 * d, R2 = 2 * dr, d2 = d * d;
+  const int d = DC > 0 ? DC : W.d, dr = DC > 0 ? DC : W.dr, D2 = 2 * d, R2 = 2 * dr, d2 = d * d;
   double *MQ = reinterpret_cast<double *>(ws + L.mq), *MP = MQ + d * D2;
   double *Qv = reinterpret_cast<double *>(ws + L.vr), *Pv = Qv + d, *qi = Pv + d, *pi = qi + d;
   double *dq = pi + d, *dQ = dq + d, *v2 = dQ + d, *PIq = v2 + d;
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(128) k_wm(EngDev E, WMDev W, WMLayout L, int m
 // K time steps per launch: the HK kernel stored the record, sqrt(det) and sign of every (step, trajectory); a group walks the
 // steps of its trajectory IN TIME ORDER (the detA / detM branch trackers are sequential) and adds the contributions of step k
 // to its own row k of partials (ngroups, K, 4) -- zeroed by the host, one writer per row
-template <int TPT>
+template <int TPT, int DC = 0>
 __global__ void __launch_bounds__(128) k_wm_fused(EngDev E, WMDev W, WMLayout L, int nsteps, double *partials) {
   extern __shared__ __align__(16) double2 wm_smem[];
   const int G = blockDim.x / TPT, gid = threadIdx.x / TPT, t = threadIdx.x % TPT;
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(128) k_wm_fused(EngDev E, WMDev W, WMLayout L,
       Es.c = E.snap_c + (size_t)step * E.n;
       Es.sign = E.snap_sign + (size_t)step * E.n;
       double acc4[4] = {0.0, 0.0, 0.0, 0.0};
-      wm_trajectory<TPT>(Es, W, L, ws, traj, WM_STEP, t, gid, acc4);
+      wm_trajectory<TPT, DC>(Es, W, L, ws, traj, WM_STEP, t, gid, acc4);
       if (t == 0) {
         double *row = partials + ((size_t)gg * nsteps + step) * 4;
         row[0] += acc4[0]; row[1] += acc4[1]; row[2] += acc4[2]; row[3] += acc4[3];
