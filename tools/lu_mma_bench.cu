@@ -20,15 +20,15 @@ static cd cpu_det(std::vector<cd> a, int n) {
   }
   return det;
 }
-template <int OCC> static float run_mma(const double2 *dA, int dr, int nmat, double2 *ddet, int ctas_per_sm) {
+template <int OCC, int NW = 4> static float run_mma(const double2 *dA, int dr, int nmat, double2 *ddet, int ctas_per_sm) {
   const size_t smem = lum_smem_bytes(dr);
-  cudaFuncSetAttribute(k_lu_mma<4, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(k_lu_mma<NW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int grid = 148 * ctas_per_sm; if (grid > nmat) grid = nmat;
-  k_lu_mma<4, OCC><<<grid, 128, smem>>>(dA, dr, nmat, ddet);
+  k_lu_mma<NW, OCC><<<grid, 32 * NW, smem>>>(dA, dr, nmat, ddet);
   cudaDeviceSynchronize();
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  k_lu_mma<4, OCC><<<grid, 128, smem>>>(dA, dr, nmat, ddet);
+  k_lu_mma<NW, OCC><<<grid, 32 * NW, smem>>>(dA, dr, nmat, ddet);
   cudaEventRecord(e1); cudaDeviceSynchronize();
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   return ms;
@@ -85,6 +85,12 @@ int main(int argc, char **argv) {
     ms = run_mma<2>(dA, dr, nmat, ddet, 2); check("DMMA occ2", ms);
     cudaMemset(ddet, 0, sizeof(double2) * nmat);
     ms = run_mma<1>(dA, dr, nmat, ddet, 1); check("DMMA occ1", ms);
+    cudaMemset(ddet, 0, sizeof(double2) * nmat);
+    ms = run_mma<3, 2>(dA, dr, nmat, ddet, 3); check("DMMA 2 warps occ3", ms);
+    cudaMemset(ddet, 0, sizeof(double2) * nmat);
+    ms = run_mma<3, 1>(dA, dr, nmat, ddet, 3); check("DMMA 1 warp occ3", ms);
+    cudaMemset(ddet, 0, sizeof(double2) * nmat);
+    ms = run_mma<3, 8>(dA, dr, nmat, ddet, 3); check("DMMA 8 warps occ3", ms);
     cudaFree(dA); cudaFree(ddet);
   }
   return 0;
