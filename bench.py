@@ -248,12 +248,12 @@ def main():
     else:
         pot = potentials.RotatedMorsePotential(T(model.omega), T(model.chi), T(model.nac), T(Q))
     pr = propagators.HermanKlukPropagator(T(G), T(G), device=device)
-    # ONE global ensemble from a fixed seed, drawn identically on every rank; each rank keeps its contiguous slice in pinned
-    # host memory so that the end-to-end leg starts from host buffers
-    torch.manual_seed(1234)
-    zi_g, probi_g = pr.sample_ensemble(T(q0), T(p0), T(G), n_total)
-    zi_pin, probi_pin = zi_g[:, lo:hi].contiguous().cpu().pin_memory(), probi_g[lo:hi].contiguous().cpu().pin_memory()
-    del zi_g, probi_g
+    # ONE global ensemble from a fixed seed: the device sampler is counter based (Philox), trajectory i of the global ensemble is
+    # a pure function of (seed, i), so every rank draws exactly its contiguous slice [lo, hi); the slice is kept in pinned host
+    # memory so that the end-to-end leg starts from host buffers
+    zi_s, probi_s = pr.sample_ensemble(T(q0), T(p0), T(G), n_local, index0=lo, seed=1234)
+    zi_pin, probi_pin = zi_s.cpu().pin_memory(), probi_s.cpu().pin_memory()
+    del zi_s, probi_s
     torch.cuda.empty_cache()
     ens_bytes = zi_pin.numel() * 8 + probi_pin.numel() * 8
 

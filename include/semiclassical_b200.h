@@ -112,6 +112,12 @@ typedef struct {
 int sc_engine_create(sc_engine **out, const sc_engine_config *cfg);
 int sc_engine_destroy(sc_engine *eng);
 
+/* initial_conditions, sampling part (propagators.py:533-555): x ~ N(0,1)^(2 d'), z = z0 + (Lz^-1)^T x, P = detLz/(2 pi)^d
+ * exp(-x.x/2) on the device with a Philox4x32-10 counter-based generator -- zi_dev (2d, n) and probi_dev (n) are a pure
+ * function of (seed, index0 + i), so ranks that pass the first global index of their shard draw ONE global ensemble.
+ * iLq_host, iLp_host: the (d' x d) blocks of Lz^-1 (propagators.py:506-515), detLz (:531). */
+int sc_engine_sample_ensemble(sc_engine *eng, int n, long long index0, unsigned long long seed, const double *iLq_host,
+                              const double *iLp_host, double detLz, double *zi_dev, double *probi_dev, void *stream);
 /* initial_conditions() after sampling (propagators.py:581-631): installs the ensemble (zi, probi), sets
  * Mqq = Mpp = 1, S = 0, t = 0, evaluates the prefactor once (initialises the sqrt branch trackers).
  * ntraj_norm is the N of the Monte-Carlo weight 1/(N probi (2 pi hbar)^d) -- the GLOBAL ensemble size when the

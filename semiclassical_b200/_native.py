@@ -97,6 +97,8 @@ _SIGNATURES = {
     "sc_engine_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(EngineConfig)]),
     "sc_engine_destroy": (ctypes.c_int, [_vp]),
     "sc_engine_set_ensemble": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_longlong, _vp, _vp, _vp]),
+    "sc_engine_sample_ensemble": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, _dp, _dp, ctypes.c_double,
+                                                 _vp, _vp, _vp]),
     "sc_engine_set_ensemble_host": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_longlong, _vp, _vp, _vp]),
     "sc_engine_step": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp]),
     "sc_engine_step_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp]),

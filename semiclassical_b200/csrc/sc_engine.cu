@@ -1073,6 +1073,34 @@ extern "C" int sc_engine_set_ensemble(sc_engine *e, int n, long long ntraj_norm,
   return SC_OK;
 }
 
+// initial_conditions: importance sampling of (qi, pi) ~ |<qi,pi,Gi|q0,p0,G0>|^2 on the device (propagators.py:533-555);
+// iLq, iLp (d' x d) are the blocks of Lz^-1 computed on the host exactly as the reference does (:506-515), detLz as :531.
+// The ensemble is a pure function of (seed, index0 + local index): ranks pass their shard's first global index.
+extern "C" int sc_engine_sample_ensemble(sc_engine *e, int n, long long index0, unsigned long long seed, const double *iLq_host,
+                                         const double *iLp_host, double detLz, double *zi_dev, double *probi_dev, void *stream) {
+  if (!e || n < 1 || !iLq_host || !iLp_host || !zi_dev || !probi_dev) return fail(SC_ERR_INVALID, "sample_ensemble(): bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int d = e->dev.d, dr = e->dev.dr;
+  const size_t m = (size_t)dr * d;
+  if (2 * m > e->stage_in_cap) {
+    CU(cudaStreamSynchronize(st));
+    if (e->stage_in) cudaFree(e->stage_in);
+    e->stage_in = nullptr;
+    e->stage_in_cap = 0;
+    CU(cudaMalloc(&e->stage_in, sizeof(double) * 2 * m));
+    e->stage_in_cap = 2 * m;
+  }
+  CU(cudaMemcpyAsync(e->stage_in, iLq_host, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(e->stage_in + m, iLp_host, sizeof(double) * m, cudaMemcpyHostToDevice, st));
+  const double pfac = detLz * std::pow(2.0 * M_PI, -(double)d);
+  k_sample_ensemble<<<(n + 3) / 4, 128, 0, st>>>(d, dr, n, index0, seed, e->stage_in, e->stage_in + m, e->dev.q0, e->dev.p0, pfac,
+                                                zi_dev, probi_dev);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(st));            // the host arrays may go away; the staging buffer may be reused
+  e->launches += 1;
+  return SC_OK;
+}
+
 extern "C" int sc_engine_set_ensemble_host(sc_engine *e, int n, long long ntraj_norm, const double *zi_host,
                                            const double *probi_host, void *stream) {
   if (!e || !zi_host || !probi_host) return fail(SC_ERR_INVALID, "null argument");

@@ -313,6 +313,90 @@ __global__ void k_init_records(EngDev E, const double *zi, const double *probi, 
   }
 }
 
+// ------------------------------------------------------------------ ensemble sampling on the device (propagators.py:533-555)
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11): key = seed, counter = (trajectory index, draw index); two
+// 53-bit uniforms per call -> two standard normals by Box-Muller.  Counter-based, so the ensemble is a pure function of
+// (seed, global trajectory index): any sharding of the index range over ranks draws the same global ensemble.
+__device__ __forceinline__ void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const unsigned n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// zi (2d, n) batch-last, probi (n):  x ~ N(0,1)^(2 d'),  z = z0 + (Lz^-1)^T x,  P = detLz / (2 pi)^d exp(-x.x / 2)
+// iLz = blockdiag(iLq, iLp): iLq, iLp (d' x d) row-major.  One warp per trajectory: lane l draws the normals l, l + 32, ...
+// and owns the components l, l + 32, ... of q and p.
+__global__ void __launch_bounds__(128)
+k_sample_ensemble(int d, int dr, int n, long long index0, unsigned long long seed, const double *__restrict__ iLq,
+                  const double *__restrict__ iLp, const double *__restrict__ q0, const double *__restrict__ p0, double pfac,
+                  double *__restrict__ zi, double *__restrict__ probi) {
+  constexpr int NE = (SC_MAX_DIM + 31) / 32;                    // components / normals per lane and half
+  const int lane = threadIdx.x & 31;
+  const int traj = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (traj >= n) return;
+  const unsigned long long gi = (unsigned long long)(index0 + traj);
+  double xq[NE], xp[NE], x2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NE; ++k) {
+    xq[k] = xp[k] = 0.0;
+    const int j = lane + 32 * k;
+    if (j < dr) {
+      unsigned c[4] = {(unsigned)gi, (unsigned)(gi >> 32), (unsigned)j, 0x5eedu};
+      philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+      // two uniforms in (0, 1]: 53 random bits each
+      const double u1 = ((double)(((unsigned long long)c[0] << 21) ^ (c[1] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+      const double u2 = ((double)(((unsigned long long)c[2] << 21) ^ (c[3] >> 11)) + 1.0) * (1.0 / 9007199254740992.0);
+      const double rad = sqrt(-2.0 * log(u1));
+      double sn, cs;
+      sincospi(2.0 * u2, &sn, &cs);
+      xq[k] = rad * cs;                                          // normal j of the position block
+      xp[k] = rad * sn;                                          // normal j of the momentum block
+      x2 += xq[k] * xq[k] + xp[k] * xp[k];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+  double zq[NE], zp[NE];
+#pragma unroll
+  for (int k = 0; k < NE; ++k) {
+    const int a = lane + 32 * k;
+    zq[k] = a < d ? q0[a] : 0.0;
+    zp[k] = a < d ? p0[a] : 0.0;
+  }
+  for (int j = 0; j < dr; ++j) {
+    const int src = j & 31, kk = j >> 5;
+    double vq = xq[0], vp = xp[0];
+#pragma unroll
+    for (int k = 1; k < NE; ++k)
+      if (kk == k) { vq = xq[k]; vp = xp[k]; }
+    vq = __shfl_sync(0xffffffffu, vq, src);
+    vp = __shfl_sync(0xffffffffu, vp, src);
+#pragma unroll
+    for (int k = 0; k < NE; ++k) {
+      const int a = lane + 32 * k;
+      if (a < d) {
+        zq[k] = fma(iLq[(size_t)j * d + a], vq, zq[k]);
+        zp[k] = fma(iLp[(size_t)j * d + a], vp, zp[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NE; ++k) {
+    const int a = lane + 32 * k;
+    if (a < d) {
+      zi[(size_t)a * n + traj] = zq[k];
+      zi[(size_t)(d + a) * n + traj] = zp[k];
+    }
+  }
+  if (lane == 0) probi[traj] = pfac * exp(-0.5 * x2);
+}
+
 // prefactor of trajectory 0 -> all trajectories (initial conditions: identical monodromy matrices)
 __global__ void k_broadcast_prefactor(double2 *c2, double2 *c, double *sign, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -144,7 +144,7 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
     seed = task.get('manual_seed', None)
     if seed is not None:
         logger.warning("The random number generator should not be seeded manually unless for debugging!")
-        torch.manual_seed(seed + rank)
+        torch.manual_seed(seed)
     calc_norm_every = task.get('calc_norm_every', 0)
     group = True if world > 1 else None
 
@@ -167,7 +167,14 @@ def run_semiclassical_dynamics(task, device='cuda', readers=None, ensembles=None
                 propagator.set_ensemble(q0, p0, Gamma_0, torch.as_tensor(zi)[:, lo:hi], torch.as_tensor(probi)[lo:hi],
                                         ntraj_total=num_samples)
             else:
-                propagator.initial_conditions(q0, p0, Gamma_0, ntraj=hi - lo, ntraj_total=num_samples)
+                # one 64-bit seed per repetition (rank 0's torch generator, hence `manual_seed`), the same on every rank: the
+                # counter-based device sampler then draws rank-independent slices [lo, hi) of ONE global ensemble
+                seed64 = torch.randint(0, 2**62, (1,), dtype=torch.int64)
+                if world > 1:
+                    seed64 = seed64.to(device)
+                    dist.broadcast(seed64, src=0)
+                propagator.initial_conditions(q0, p0, Gamma_0, ntraj=hi - lo, ntraj_total=num_samples, index0=lo,
+                                              seed=int(seed64.item()))
         _, err = guarded(install)
         agree(err)
         autocorrelation_ = np.zeros((nt,), dtype=complex)

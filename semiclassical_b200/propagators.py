@@ -225,7 +225,7 @@ class HermanKlukPropagator(object):
         self._const_key, self._const_dims = key, (d, dr)
         return d, dr
 
-    def initial_conditions(self, q0, p0, Gamma_0, ntraj=5000, ntraj_total=None):
+    def initial_conditions(self, q0, p0, Gamma_0, ntraj=5000, ntraj_total=None, index0=0, seed=None):
         """
         sample initial positions and momenta from P(qi,pi) ~ |<qi,pi,Gamma_i|q0,p0,Gamma_0>|^2
         (propagators.py:445-631) and install them on the device
@@ -234,14 +234,17 @@ class HermanKlukPropagator(object):
         """
         assert Gamma_0.size() == self.Gamma_i.size(), "Width parameter matrix Gamma_0 has wrong dimensions."
         assert _is_symmetric_non_negative(Gamma_0), "Gamma_0 has to be symmetric and positive semi-definite."
-        zi, probi = self.sample_ensemble(q0, p0, Gamma_0, ntraj)
+        zi, probi = self.sample_ensemble(q0, p0, Gamma_0, ntraj, index0=index0, seed=seed)
         self._install(zi, probi, ntraj_total)
 
-    def sample_ensemble(self, q0, p0, Gamma_0, ntraj):
+    def sample_ensemble(self, q0, p0, Gamma_0, ntraj, index0=0, seed=None):
         """
-        draws ntraj phase-space points from P(qi,pi) ~ |<qi,pi,Gamma_i|q0,p0,Gamma_0>|^2 with torch's CUDA generator
-        (propagators.py:493-555) WITHOUT installing them: returns zi (2 dim, ntraj), probi (ntraj,) on the device.  Ranks that
-        seed the generator identically draw the same global ensemble and install their slice with set_ensemble().
+        draws ntraj phase-space points from P(qi,pi) ~ |<qi,pi,Gamma_i|q0,p0,Gamma_0>|^2 (propagators.py:493-555) WITHOUT
+        installing them: returns zi (2 dim, ntraj), probi (ntraj,) on the device.  Sampling runs in the engine's own kernel
+        (Philox4x32-10 counter-based generator + Box-Muller, k_sample_ensemble): the ensemble is a pure function of
+        (seed, index0 + i).  seed=None draws the 64-bit seed from torch's default CPU generator, so torch.manual_seed(s)
+        makes runs reproducible as in the reference; ranks that seed identically and pass the first global index of their
+        shard as index0 draw slices of ONE global ensemble.
         """
         self._prepare(q0, p0, Gamma_0)
         d = self.dim
@@ -256,13 +259,17 @@ class HermanKlukPropagator(object):
         assert int(nzp.sum()) == int(nzq.sum()), \
             "number of non-zero modes for sampling of positions and momenta have to be the same"
         nnz = int(nzp.sum())
-        iLz = torch.block_diag(iLq, iLp).to(self.device)
+        assert nnz == self.rank
         detLz = torch.prod(2 * torch.sqrt(wq[nzq] / wp[nzp])).item()
-        # x ~ N(0,1)^(2 d'), z = z0 + (Lz^-1)^T x
-        xi = torch.randn((ntraj, 2 * nnz), dtype=torch.float64, device=self.device).T
-        z0 = torch.cat((self.q0, self.p0))
-        zi = z0.unsqueeze(1) + torch.einsum('ji,jn->in', iLz, xi)
-        probi = detLz / (2 * np.pi)**d * torch.exp(-0.5 * torch.einsum('in,in->n', xi, xi))
+        if seed is None:
+            seed = int(torch.randint(0, 2**62, (1,), dtype=torch.int64).item())
+        zi = torch.empty((2 * d, ntraj), dtype=torch.float64, device=self.device)
+        probi = torch.empty(ntraj, dtype=torch.float64, device=self.device)
+        a_q, a_p = _np(iLq), _np(iLp)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().sc_engine_sample_ensemble(self._engine, int(ntraj), int(index0), int(seed), _ptr(a_q), _ptr(a_p),
+                                                                  float(detLz), zi.data_ptr(), probi.data_ptr(), self._stream()))
+        self._iLz_detLz = (iLq, iLp, detLz)
         logger.info("== Initial Conditions ==")
         logger.info(f"number of dimensions   :  {d}")
         logger.info(f"zero dimensions        :  {d - nnz}")

@@ -419,6 +419,41 @@ def test_norm_against_oracle_ragged(cuda_device):
     assert relerr(pr.wavefunction(T(x)), oracle.hk_wavefunction(G, qpS, v, x)) < TOL
 
 
+# ------------------------------------------------------------------ on-device ensemble sampling (propagators.py:493-555)
+@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium", "hk_as24_rot"])
+def test_device_sampler(name, cuda_device):
+    """k_sample_ensemble (Philox4x32-10 + Box-Muller) behind initial_conditions: the ensemble is a pure function of
+    (seed, global index) -- shards concatenate bitwise to the unsharded draw; probi is exactly the density of the recovered
+    normals (diagonal, rank-deficient d' = 6 of 12, and dense widths); moments and a Kolmogorov-Smirnov test of the normals"""
+    from scipy import stats
+    from semiclassical_b200 import propagators
+    g = helpers.load_golden(name)
+    pr = propagators.HermanKlukPropagator(T(g['Gamma_i']), T(g['Gamma_t']), device=cuda_device)
+    q0, p0, G0 = T(g['q0']), T(g['p0']), T(g['Gamma_0'])
+    n = 100000
+    zi, probi = pr.sample_ensemble(q0, p0, G0, n, seed=77)
+    za, pa = pr.sample_ensemble(q0, p0, G0, 40001, index0=0, seed=77)
+    zb, pb = pr.sample_ensemble(q0, p0, G0, n - 40001, index0=40001, seed=77)
+    assert torch.equal(torch.cat((za, zb), dim=1), zi) and torch.equal(torch.cat((pa, pb)), probi)
+    z2, _ = pr.sample_ensemble(q0, p0, G0, 1000, seed=78)
+    assert not torch.equal(z2, zi[:, :1000])
+    # recover the normals: zi - z0 = (Lz^-1)^T x  (least squares: exact in the sampled subspace)
+    iLq, iLp, detLz = pr._iLz_detLz
+    d, dr = pr.dim, pr.rank
+    iLz = np.zeros((2 * dr, 2 * d))
+    iLz[:dr, :d], iLz[dr:, d:] = iLq.numpy(), iLp.numpy()
+    dz = zi.cpu().numpy() - np.concatenate((g['q0'], g['p0']))[:, None]
+    x, res, _, _ = np.linalg.lstsq(iLz.T, dz, rcond=None)
+    assert np.abs(iLz.T @ x - dz).max() < 1e-10 * max(1.0, np.abs(dz).max())
+    pref = detLz / (2 * np.pi) ** d
+    assert np.abs(probi.cpu().numpy() / (pref * np.exp(-0.5 * (x * x).sum(axis=0))) - 1.0).max() < 1e-9
+    # statistics of the 2 d' normals
+    assert np.abs(x.mean(axis=1)).max() < 5.0 / np.sqrt(n)
+    assert np.abs(np.cov(x) - np.eye(2 * dr)).max() < 6.0 / np.sqrt(n)
+    for j in (0, dr - 1, dr, 2 * dr - 1):
+        assert stats.kstest(x[j], 'norm').pvalue > 1e-4
+
+
 # ------------------------------------------------------------------ `semi dynamics` driver (cli.py:171-476)
 def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
     """the JSON-task driver on the 5-mode AS fixture with the reference's ensemble injected: same correlations.npz
