@@ -531,6 +531,32 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
+@pytest.mark.parametrize("d,n,nt", [(17, 1, 4), (18, 2, 5), (31, 149, 4), (32, 3, 37), (33, 150, 3), (47, 297, 3), (61, 5, 4), (65, 7, 3),
+                                    (80, 151, 3)])
+def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
+    """ragged shapes of the dense column pipeline: smallest d, d not a multiple of 4 / 8, one or two trajectories (fewer than
+    SMs, than warps of a path CTA), ensembles that are not a multiple of the SM count, more steps than one pass holds (37 > 16:
+    three passes over the state), tile groups with a ragged last group (d = 65: 17 tiles over 8-warp CTAs)"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.harmonic_molecule_synthetic(d)
+    G = m['Gamma_0']
+    zi, probi = oracle.sample_ensemble(G, G, m['q0'], m['p0'], n, np.random.default_rng(500 + d))
+    dt, _ = workloads.test_time_grid()
+    opot = oracle.Potential.harmonic(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    ref = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt + 1, m['en_zpt'])
+    pot = potentials.MolecularHarmonicPotential.from_arrays(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m['q0']), T(m['p0']), T(G), T(zi), T(probi))
+    a, i = pr.propagate(pot, dt, nt, m['en_zpt'])
+    assert pr.kernel_name().startswith("k_rk4_stream+k_rmult+")
+    assert relerr(a, ref['autocorrelation'][1:]) < TOL
+    assert relerr(i, ref['ic_correlation'][1:]) < TOL
+    pr.step(pot, dt)                                   # the oracle loop of nt + 1 reads ends with one more step
+    assert relerr(pr.y.cpu().numpy(), ref['y']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
+
+
 @pytest.mark.parametrize("name", ["hk_as24_rot", "hk_as60_rot"])
 def test_rotated_models_run_on_the_stream_pipeline(name, cuda_device):
     """per-trajectory dense Hessians (Q diag(h) Q^T formed by k_expand_hessian) + dense width matrices: the reference's own
