@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--no-dense-legs", action="store_true", help="skip the roofline_dense legs")
     ap.add_argument("--dense-ntraj", type=int, default=148000, help="ensemble of the harmonic / rotated roofline_dense legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-mma", action="store_true", help="force the DFMA kernel (diagnostics)")
+    ap.add_argument("--no-mma", action="store_true", help="force the DFMA kernel k_hk_generic (diagnostics)")
     args = ap.parse_args()
 
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":

@@ -378,86 +378,7 @@ __device__ __forceinline__ double2 lu_det_cta(double2 *Cm, int dr, unsigned *wke
   return det;
 }
 
-// Second CTA-wide variant, organised for a low instruction count (the elimination is issue-bound, not
-// flop-bound): thread (r, c) owns row r = t % 64 and the columns j == c (mod NS), NS = TPT / 64.  The row
-// stride ldc is odd (in complex elements) so that the 32 rows of a warp hit distinct banks; the pivot-row
-// element u[j] is a broadcast load.  One barrier per column as in lu_det_cta.
-template <int TPT>
-__device__ __forceinline__ double2 lu_det_rc(double2 *Cm, int dr, int ldc, unsigned *wkey, int t) {
-  static_assert(TPT % 64 == 0, "lu_det_rc needs a multiple of 64 threads");
-  constexpr int NW = TPT / 32, NS = TPT / 64;
-  const int lane = t & 31, warp = t >> 5;
-  const int r = t & 63, c = t >> 6;
-  const bool active = r < dr;
-  double2 *rowp = Cm + (active ? r : dr - 1) * ldc;
-  unsigned long long done = 0ull;
-  double2 det = make_double2(1.0, 0.0);
-  int inversions = 0;
-  {
-    unsigned key = (c == 0 && active) ? pivot_key(rowp[0], r) : 0u;
-    key = __reduce_max_sync(0xffffffffu, key);
-    if (lane == 0) wkey[warp] = key;
-  }
-  __syncthreads();
-  for (int k = 0; k < dr; ++k) {
-    const unsigned *wk = wkey + (k & 1) * 32;
-    unsigned kk = (lane < NW) ? wk[lane] : 0u;
-    const double2 ak = rowp[k];
-    kk = __reduce_max_sync(0xffffffffu, kk);
-    const int p = static_cast<int>(kk & 63u);
-    inversions += __popcll(done >> p);          // earlier pivots with a larger row index
-    done |= 1ull << p;
-    const double2 *prow = Cm + p * ldc;
-    const double2 pv = prow[k];
-    det = cmul(det, pv);
-    if (k + 1 == dr) break;
-    const double rn = 1.0 / (pv.x * pv.x + pv.y * pv.y);
-    const double2 f = cmul(ak, make_double2(pv.x * rn, -pv.y * rn));
-    const bool mine = active && !((done >> r) & 1ull);
-    // first owned column beyond k
-    int j = c + NS * ((k + 1 - c + NS - 1 >= 0 ? (k + 1 - c + NS - 1) : 0) / NS);
-    unsigned nkey = 0u;
-    if (j == k + 1) {
-      const double2 u = prow[j];
-      double2 v = rowp[j];
-      v.x -= f.x * u.x - f.y * u.y;
-      v.y -= f.x * u.y + f.y * u.x;
-      if (mine) { rowp[j] = v; nkey = pivot_key(v, r); }
-      j += NS;
-    }
-#pragma unroll 2
-    for (; j < dr; j += NS) {
-      const double2 u = prow[j];
-      double2 v = rowp[j];
-      v.x -= f.x * u.x - f.y * u.y;
-      v.y -= f.x * u.y + f.y * u.x;
-      if (mine) rowp[j] = v;
-    }
-    nkey = __reduce_max_sync(0xffffffffu, nkey);
-    if (lane == 0) wkey[((k + 1) & 1) * 32 + warp] = nkey;
-    __syncthreads();
-  }
-  if (inversions & 1) { det.x = -det.x; det.y = -det.y; }
-  return det;
-}
-
-// ------------------------------------------------------------------ register-resident LU -----
-// Third CTA-wide variant: the matrix never touches shared memory.  NW warps take part; warp w owns the columns
-// j == w (mod NW) (MC of them), lane l owns the rows l ("lo") and l + 32 ("hi"): each thread holds 2 x MC
-// complex elements in registers.  Per column k exactly ONE barrier:
-//   - the warp that owns column k+1 updates that column first, finds its pivot with redux.sync on a packed
-//     (magnitude, row) key, and publishes the column, the pivot index and the reciprocal pivot (computed
-//     speculatively for every candidate while the redux is in flight) to a double-buffered 1 KB area
-//   - after the barrier every thread reads its two multipliers a[r][k] / pivot and gets the pivot-row elements
-//     of its own columns by warp shuffle from lane p % 32 (the pivot row lives in the same lane of every warp)
-// Rows are never moved: retired rows are tracked in a 64-bit mask, the permutation parity by popcounts.
-// Since det A = det A^T the callers are free to load the transpose (whichever is conflict-free to read).
-struct LuShared {
-  double2 col[2][64];
-  double2 ipv[2], pv[2];
-  int p[2], pad[2];
-};
-
+// named barrier of the blocked LU kernels (sc_lu.cuh): id 0 is __syncthreads
 __device__ __forceinline__ unsigned lu_key(double m, int row) {
   return (static_cast<unsigned>(__double2hiint(m)) & ~63u) + 64u + static_cast<unsigned>(row);
 }
@@ -466,92 +387,6 @@ template <int BAR_ID, int NTHR>
 __device__ __forceinline__ void lu_bar() {
   if (BAR_ID == 0) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"n"(BAR_ID), "n"(NTHR) : "memory");
-}
-
-__device__ __forceinline__ void lu_publish(double2 clo, double2 chi, unsigned long long done, int dr, LuShared *sh,
-                                           int b, int lane) {
-  const double mlo = clo.x * clo.x + clo.y * clo.y, mhi = chi.x * chi.x + chi.y * chi.y;
-  unsigned key = 0u;
-  if (lane < dr && !((done >> lane) & 1ull)) key = lu_key(mlo, lane);
-  if (lane + 32 < dr && !((done >> (lane + 32)) & 1ull)) key = max(key, lu_key(mhi, lane + 32));
-  // speculative reciprocals (overlap the redux latency); exact zeros (structurally sparse matrices are common:
-  // separable models give a diagonal prefactor matrix) must not fall into the division slow path
-  const double rlo = 1.0 / (mlo == 0.0 ? 1.0 : mlo), rhi = 1.0 / (mhi == 0.0 ? 1.0 : mhi);
-  const unsigned kk = __reduce_max_sync(0xffffffffu, key);
-  const int p = static_cast<int>(kk & 63u);
-  sh->col[b][lane] = clo;
-  sh->col[b][lane + 32] = chi;
-  if (lane == (p & 31)) {
-    const bool h = p >= 32;
-    const double2 c = h ? chi : clo;
-    const double r = h ? rhi : rlo;
-    sh->ipv[b] = make_double2(c.x * r, -c.y * r);
-    sh->pv[b] = c;
-    sh->p[b] = p;
-  }
-}
-
-// lo[m], hi[m]: elements (row lane / lane+32, column w + NW m); entries outside dr x dr must be zero.
-// Result valid on every participating thread.
-template <int NW, int MC, int BAR_ID>
-__device__ __forceinline__ double2 lu_det_regs(double2 (&lo)[MC], double2 (&hi)[MC], int dr, LuShared *sh, int w,
-                                               int lane) {
-  const bool use_hi = dr > 32;
-  unsigned long long done = 0ull;
-  double2 det = make_double2(1.0, 0.0);
-  int inversions = 0;
-  bool finished = false;
-  if (w == 0) lu_publish(lo[0], hi[0], done, dr, sh, 0, lane);
-  lu_bar<BAR_ID, 32 * NW>();
-#pragma unroll
-  for (int kb = 0; kb < MC; ++kb) {
-#pragma unroll 1
-    for (int kk = 0; kk < NW; ++kk) {
-      const int k = kb * NW + kk;
-      if (finished || k >= dr) { finished = true; break; }
-      const int b = k & 1;
-      const int p = sh->p[b];
-      const double2 ipv = sh->ipv[b], pv = sh->pv[b];
-      const double2 alo = sh->col[b][lane], ahi = sh->col[b][lane + 32];
-      det = cmul(det, pv);
-      inversions += __popcll(done >> p);          // earlier pivots with a larger row index
-      done |= 1ull << p;
-      if (k + 1 == dr) { finished = true; break; }
-      if (pv.x == 0.0 && pv.y == 0.0) { finished = true; break; }   // singular: det == 0 (uniform exit)
-      // multipliers; retired rows (including the pivot row) are left alone
-      double2 flo = cmul(alo, ipv), fhi = cmul(ahi, ipv);
-      if ((done >> lane) & 1ull) flo = make_double2(0.0, 0.0);
-      if ((done >> (lane + 32)) & 1ull) fhi = make_double2(0.0, 0.0);
-      const int src = p & 31;
-      const bool ph = p >= 32;
-      auto update = [&](double2 &l, double2 &h) {
-        double ux = ph ? h.x : l.x, uy = ph ? h.y : l.y;
-        ux = __shfl_sync(0xffffffffu, ux, src);
-        uy = __shfl_sync(0xffffffffu, uy, src);
-        l.x = fma(-flo.x, ux, fma(flo.y, uy, l.x));
-        l.y = fma(-flo.x, uy, fma(-flo.y, ux, l.y));
-        if (use_hi) {
-          h.x = fma(-fhi.x, ux, fma(fhi.y, uy, h.x));
-          h.y = fma(-fhi.x, uy, fma(-fhi.y, ux, h.y));
-        }
-      };
-      if (w > kk) update(lo[kb], hi[kb]);
-      if (kb + 1 < MC) update(lo[kb + 1 < MC ? kb + 1 : kb], hi[kb + 1 < MC ? kb + 1 : kb]);
-      // look-ahead: the owner of column k+1 publishes it before touching its remaining columns
-      const bool wrap = (kk + 1 == NW);
-      if (w == (wrap ? 0 : kk + 1)) {
-        const int mn = (wrap && kb + 1 < MC) ? kb + 1 : kb;
-        double2 clo = lo[kb], chi = hi[kb];
-        if (mn != kb) { clo = lo[kb + 1 < MC ? kb + 1 : kb]; chi = hi[kb + 1 < MC ? kb + 1 : kb]; }
-        lu_publish(clo, chi, done, dr, sh, (k + 1) & 1, lane);
-      }
-#pragma unroll
-      for (int m = kb + 2; m < MC; ++m) update(lo[m], hi[m]);
-      lu_bar<BAR_ID, 32 * NW>();
-    }
-  }
-  if (inversions & 1) { det.x = -det.x; det.y = -det.y; }
-  return det;
 }
 
 // ------------------------------------------------------------------ prefactor assembly -------

@@ -526,14 +526,12 @@ struct LaunchPlan {
   int tpt, ept, groups_per_cta, threads, grid;
   size_t smem;
   SmemLayout L;
-  bool mma;
 };
 
-static int plan_launch(const sc_engine *e, int mode, bool allow_mma, LaunchPlan &pl) {
+static int plan_launch(const sc_engine *e, LaunchPlan &pl) {
   const int d = e->dev.d, dr = e->dev.dr, n = e->dev.n;
   const int ne = 2 * d * d;
-  pl.mma = false;
-  int ldu = 2 * d, ldh = d;
+  const int ldu = 2 * d, ldh = d;
   if (d <= 16) {
     pl.tpt = 32; pl.groups_per_cta = 4; pl.threads = 128;
     pl.ept = (ne + 31) / 32;
@@ -541,13 +539,8 @@ static int plan_launch(const sc_engine *e, int mode, bool allow_mma, LaunchPlan 
     pl.tpt = (d <= 45) ? 256 : 320;
     pl.groups_per_cta = 1; pl.threads = pl.tpt;
     pl.ept = (ne + pl.tpt - 1) / pl.tpt;
-    if (allow_mma && mode == MODE_STEP && mma_supported(d)) {
-      pl.mma = true;
-      mma_leading_dims(d, ldu, ldh);
-      pl.tpt = pl.threads = mma_threads(d);
-    }
   }
-  pl.L = make_layout(d, dr, ldu, ldh, pl.mma ? MMA_KMAX : 0);
+  pl.L = make_layout(d, dr, ldu, ldh, 0);
   pl.smem = sizeof(double) * (size_t)pl.L.total * pl.groups_per_cta;
   if (pl.smem > 227 * 1024) return fail(SC_ERR_UNSUPPORTED, "shared-memory footprint %zu B exceeds 227 KB (d = %d)", pl.smem, d);
   const int groups_needed = n;
@@ -839,9 +832,11 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
             CU(cudaGetLastError());
             e->launches += 2;
           }
-      } else if ((P.type == POT_MORSE || P.type == POT_NONHARMONIC) && e->dev.diag) {
+      } else if ((P.type == POT_MORSE || P.type == POT_NONHARMONIC) && e->dev.diag && d <= 64) {
         k_qp_path<<<(nt + 3) / 4, 128, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, hd, aux);      // overlap terms included
         aux_done = true;
+      } else if (P.type == POT_MORSE || P.type == POT_NONHARMONIC) {
+        k_path_separable<<<(nt + PATH_WARPS - 1) / PATH_WARPS, 32 * PATH_WARPS, 0, st>>>(e->dev, P, h, ks, (int)t0, nt, qp, aux, hd);
       } else {
         return fail(SC_ERR_UNSUPPORTED, "stream pipeline: potential type %d", P.type);
       }
@@ -884,77 +879,20 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   return SC_OK;
 }
 
-// k_hk_mma in split mode + batched LU + finish kernel: the general (dense Gamma, any native potential) path for
-// 17 <= d <= 62.  Same batching as run_hk_chunked: windows of ntb trajectories x passes of KC steps, scratch for the
-// prefactor matrices of one window.
-static int run_hk_mma_split(sc_engine *e, const PotDev &P, double h, int nsteps, double *out_dev, cudaStream_t st,
-                            const LaunchPlan &pl) {
-  const int n = e->dev.n, dr = e->dev.dr, sm = e->sm_count;
-  int KC = 16;
-  if (const char *s = getenv("SC_CHUNK_K")) KC = atoi(s) > 0 ? atoi(s) : KC;
-  if (KC > MMA_KMAX) KC = MMA_KMAX;
-  {
-    const int npass = (nsteps + KC - 1) / KC;
-    KC = (nsteps + npass - 1) / npass;
-  }
-  const size_t per_traj = (size_t)KC * ((size_t)dr * dr * sizeof(double2) + sizeof(double2) + 8 * sizeof(double));
-  size_t budget = (size_t)3 << 30;
-  if (const char *s = getenv("SC_CHUNK_SCRATCH_MB")) budget = (size_t)atol(s) << 20;
-  long long ntb = (long long)(budget / per_traj);
-  ntb = (ntb / sm) * sm;
-  if (ntb < sm) ntb = sm;
-  if (ntb > n) ntb = n;
-  const size_t need_bytes = per_traj * (size_t)ntb + 512;
-  if (need_bytes > e->chunk_scratch_cap) {
-    CU(cudaStreamSynchronize(st));
-    if (e->chunk_scratch) cudaFree(e->chunk_scratch);
-    e->chunk_scratch = nullptr;
-    CU(cudaMalloc(&e->chunk_scratch, need_bytes));
-    e->chunk_scratch_cap = need_bytes;
-  }
-  double2 *cm = reinterpret_cast<double2 *>(e->chunk_scratch);
-  double2 *det = cm + (size_t)KC * ntb * dr * dr;
-  double *aux = reinterpret_cast<double *>(det + (size_t)KC * ntb);
-  size_t ngroups = 0;
-  for (long long t0 = 0; t0 < n; t0 += ntb) ngroups += (size_t)((std::min<long long>(ntb, n - t0) + 127) / 128);
-  if (int rc = ensure_partials(e, ngroups * nsteps * 5, st)) return rc;
-  for (int s0 = 0; s0 < nsteps; s0 += KC) {
-    const int ks = std::min(KC, nsteps - s0);
-    size_t g0 = 0;
-    for (long long t0 = 0; t0 < n; t0 += ntb) {
-      const int nt = (int)std::min<long long>(ntb, n - t0);
-      const int grid = std::min(nt, pl.grid);
-      cudaError_t ce = launch_mma(grid, pl.threads, pl.smem, e->dev, P, h, ks, nullptr, pl.L, st, (int)t0, nt, cm, aux);
-      if (ce != cudaSuccess) return fail(SC_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(ce));
-      CU(launch_lu_batch(cm, dr, ks * nt, det, sm, 0, st));
-      const int nblk = (nt + 127) / 128;
-      k_hk_finish<<<nblk, 128, 0, st>>>(e->dev, (int)t0, nt, ks, s0, nsteps, det, aux, e->partials + g0 * nsteps * 5);
-      CU(cudaGetLastError());
-      g0 += nblk;
-      e->launches += 3;
-    }
-  }
-  k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
-  CU(cudaGetLastError());
-  e->launches += 1;
-  e->kernel_name = dr > 32 ? "k_hk_mma+k_lu_mma+k_hk_finish" : "k_hk_mma+k_lu_batch+k_hk_finish";
-  return SC_OK;
-}
-
 static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, int mode, double *out_dev, cudaStream_t st,
                          bool allow_mma = true) {
   LaunchPlan pl;
   if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
   if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && !e->dense_engine && !getenv("SC_DENSE_ENGINE") && chunk_supported(e->dev, P))
     return run_hk_chunked(e, P, h, nsteps, out_dev, st);
-  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P, e->dense_engine || getenv("SC_DENSE_ENGINE")))
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
     return run_hk_stream(e, P, h, nsteps, out_dev, st);
   if (e->dev.d > 62) {                       // the set-up / read-out modes of k_hk_generic do not fit in shared memory
     if (mode == MODE_INIT || mode == MODE_TRACK) return run_prefactor_stream(e, mode, st);
     if (mode == MODE_CORR) return run_corr_now(e, out_dev, st);
     return fail(SC_ERR_UNSUPPORTED, "no fused step kernel for this potential at d = %d; use the stage interface", e->dev.d);
   }
-  if (int rc = plan_launch(e, mode, allow_mma, pl)) return rc;
+  if (int rc = plan_launch(e, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;
   const size_t need = (size_t)ngroups * nrows * 5;
@@ -965,14 +903,9 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
     CU(cudaMalloc(&e->partials, sizeof(double) * need));
     e->partials_cap = need;
   }
-  if (mode != MODE_INIT && mode != MODE_TRACK && !pl.mma) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
+  if (mode != MODE_INIT && mode != MODE_TRACK) CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
   cudaError_t ce = cudaSuccess;
-  if (pl.mma && mode == MODE_STEP && !getenv("SC_MMA_FUSED_LU")) return run_hk_mma_split(e, P, h, nsteps, out_dev, st, pl);
-  if (pl.mma) {
-    ce = launch_mma(pl.grid, pl.threads, pl.smem, e->dev, P, h, nsteps, e->partials, pl.L, st);
-    e->kernel_name = "k_hk_mma";
-    e->launches += (nsteps - 1) / MMA_KMAX;
-  } else {
+  {
     e->kernel_name = "k_hk_generic";
 #define CASE(T, E_) ce = launch_generic<T, E_>(pl, e->dev, P, h, nsteps, mode, e->partials, st)
     if (pl.tpt == 32) {
@@ -1133,7 +1066,7 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
   if (nsteps < 1) return SC_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (int rc = set_nac(e, pot->n1.data(), st)) return rc;
-  if (pot->dev.type == POT_GDML && !stream_supported(e->dev, pot->dev, false))
+  if (pot->dev.type == POT_GDML && !stream_supported(e->dev, pot->dev))
     return fail(SC_ERR_UNSUPPORTED, "sGDML potentials with d < 17 or d > 64 run through the stage interface");
   if (!corr_dev) {
     if (int rc = ensure_corr(e, nsteps, st)) return rc;
@@ -1646,16 +1579,3 @@ extern "C" int sc_engine_get_timing_slots(sc_engine *e, double *ms, int nslots) 
 
 // ------------------------------------------------------------------ generic-potential stage path
 #include "sc_stage.cuh"
-
-// ------------------------------------------------------------------ diagnostics
-#ifdef SC_PHASE_TIMING
-extern "C" int sc_debug_phase_cycles(unsigned long long *out16, int reset) {
-  CU(cudaDeviceSynchronize());
-  CU(cudaMemcpyFromSymbol(out16, sc::g_phase_cycles, sizeof(unsigned long long) * 16));
-  if (reset) {
-    unsigned long long z[16] = {0};
-    CU(cudaMemcpyToSymbol(sc::g_phase_cycles, z, sizeof(z)));
-  }
-  return SC_OK;
-}
-#endif

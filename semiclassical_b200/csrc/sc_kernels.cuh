@@ -26,8 +26,6 @@ struct SmemLayout {
   int off_Ub, off_Vb, off_Us, off_H, off_vec, off_red, off_int, off_lu, off_acc, total;  // in doubles, per group
 };
 
-// mma_kmax > 0: layout of the tensor-core kernel (register LU exchange area, shared correlation accumulators
-// for mma_kmax time steps per launch)
 __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ldh, int mma_kmax = 0) {
   SmemLayout L;
   L.ldu = ldu;
@@ -47,11 +45,7 @@ __host__ __device__ inline SmemLayout make_layout(int d, int dr, int ldu, int ld
   L.off_int = o; o += (dr < 32 ? 38 : (dr + 6) & ~1);  // LU bookkeeping (2 dr ints | 64 keys) + pivot inverse (double2)
   o = (o + 1) & ~1;
   L.off_lu = o; L.off_acc = o;
-  if (mma_kmax > 0) {
-    o += (int)((sizeof(LuShared) + 7) / 8);
-    o = (o + 1) & ~1;
-    L.off_acc = o; o += 5 * mma_kmax;
-  }
+  (void)mma_kmax;
   L.total = (o + 1) & ~1;
   return L;
 }

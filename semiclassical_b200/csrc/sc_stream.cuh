@@ -562,6 +562,83 @@ k_path_harmonic(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, do
   if (lane == 0) rec[2 * d] = S;
 }
 
+// separable potentials (Morse / AS, NonHarmonic) with ANY width matrices: like k_qp_path (sc_chunk.cuh) without its
+// diagonal-width overlap terms (k_aux_terms computes them from the stored q, p).  hd (step, tl, 4, dp): stage Hessian diagonals.
+__global__ void __launch_bounds__(32 * PATH_WARPS)
+k_path_separable(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, double *__restrict__ qp, double *__restrict__ aux,
+                 double *__restrict__ hd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = E.d, dp = (d + 1) & ~1;
+  const int tl = blockIdx.x * PATH_WARPS + warp;
+  if (tl >= ntb) return;
+  double *rec = E.rec + (size_t)(traj0 + tl) * E.rs;
+  double q[PATH_NE], p[PATH_NE], im[PATH_NE];
+#pragma unroll
+  for (int k = 0; k < PATH_NE; ++k) {
+    const int a = lane + 32 * k;
+    const bool ok = a < d;
+    q[k] = ok ? rec[a] : 0.0;
+    p[k] = ok ? rec[d + a] : 0.0;
+    im[k] = ok ? P.imass[a] : 0.0;
+  }
+  double S = rec[2 * d];
+  for (int step = 0; step < nsteps; ++step) {
+    double *hrow = hd + ((size_t)step * ntb + tl) * 4 * dp;
+    double accS = 0.0, e4 = 0.0;
+#pragma unroll
+    for (int k = 0; k < PATH_NE; ++k) {
+      const int a = lane + 32 * k;
+      if (a < d) {
+        const double qa = q[k], pa = p[k];
+        double qsa = qa, psa = pa, accq = 0.0, accp = 0.0;
+#pragma unroll
+        for (int s = 1; s <= 4; ++s) {
+          const double cnext = (s == 3) ? h : 0.5 * h;
+          const double wgt = (s == 1 || s == 4) ? 1.0 : 2.0;
+          double gt, hdg;
+          const double vpart = pot_local_vals(P, a, qsa, gt, hdg);
+          hrow[(s - 1) * dp + a] = hdg;
+          const double kq = psa * im[k], kp = -gt;
+          const double tk = 0.5 * psa * psa * im[k];
+          accS += wgt * (tk - vpart);
+          if (s == 4) e4 += tk + vpart;
+          accq += wgt * kq;
+          accp += wgt * kp;
+          if (s < 4) {
+            qsa = qa + cnext * kq;
+            psa = pa + cnext * kp;
+          }
+        }
+        q[k] = qa + h / 6.0 * accq;
+        p[k] = pa + h / 6.0 * accp;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      accS += __shfl_xor_sync(0xffffffffu, accS, o);
+      e4 += __shfl_xor_sync(0xffffffffu, e4, o);
+    }
+    S += h / 6.0 * accS;
+    double *qo = qp + ((size_t)step * ntb + tl) * 2 * d;
+#pragma unroll
+    for (int k = 0; k < PATH_NE; ++k) {
+      const int a = lane + 32 * k;
+      if (a < d) { qo[a] = q[k]; qo[d + a] = p[k]; }
+    }
+    if (lane == 0) {
+      double *ax = aux + ((size_t)step * ntb + tl) * 8;
+      ax[6] = S;
+      ax[7] = e4;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PATH_NE; ++k) {
+    const int a = lane + 32 * k;
+    if (a < d) { rec[a] = q[k]; rec[d + a] = p[k]; }
+  }
+  if (lane == 0) rec[2 * d] = S;
+}
+
 // rotated Morse potential (dense parity fixture): V'(x) = V(Q^T x); r = Q^T x, inner Morse per mode,
 // grad = Q g.  One warp per trajectory; the inner second derivatives h_k of every stage go to hd (step, tl, 4, dp) --
 // k_expand_hessian forms H_s = Q diag(h_s) Q^T on the tensor pipe.  Q in shared memory with an odd leading dimension
@@ -970,14 +1047,14 @@ k_corr_now(EngDev E, double *__restrict__ partials) {
   }
 }
 
-// dense_engine: separable models too (their diagonal Hessians are expanded to full matrices: the kernel multiplies
-// whatever it is given; sc_chunk.cuh is the path that knows about the structure)
-static bool stream_supported(const EngDev &E, const PotDev &P, bool dense_engine) {
+// separable models too: their diagonal stage Hessians are expanded to full matrices (the kernel multiplies whatever it is
+// given).  With diagonal full-rank widths and d > 32 the structured pipeline of sc_chunk.cuh is faster and is preferred by
+// the dispatcher unless the dense engine is asked for (option dense_engine)
+static bool stream_supported(const EngDev &E, const PotDev &P) {
   if (E.d < 17 || E.d > SC_MAX_DIM) return false;
   if (P.type == POT_HARMONIC) return true;
   if (E.d > 64) return false;                  // Hessian expansion / sGDML kernels: d <= 64
-  if (P.type == POT_ROTATED_MORSE || P.type == POT_GDML) return true;
-  return dense_engine && E.diag && E.dr == E.d && (P.type == POT_MORSE || P.type == POT_NONHARMONIC);
+  return P.type == POT_ROTATED_MORSE || P.type == POT_GDML || P.type == POT_MORSE || P.type == POT_NONHARMONIC;
 }
 
 }  // namespace sc

@@ -1,4 +1,4 @@
-"""throughput of the general path (k_hk_mma split + batched LU) on a synthetic harmonic 'molecule': dense Hessian,
+"""throughput of the dense column pipeline (sc_stream.cuh) on a synthetic harmonic 'molecule': dense Hessian,
 dense width matrices with 6 zero modes (d' = d - 6), the shape of the reference's molecular use case (C3 at size d)
 usage: dense_probe.py [d] [ntraj] [nsteps]"""
 import os, sys, json
