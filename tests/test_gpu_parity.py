@@ -557,6 +557,34 @@ def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
 
 
+@pytest.mark.parametrize("d", [20, 40])
+def test_separable_potential_with_dense_widths(d, cuda_device):
+    """AS (Morse) potential -- diagonal Hessian -- with DENSE width matrices (a wavepacket whose widths are not aligned with the
+    modes): k_path_separable + k_aux_terms + expanded diagonal Hessians + the dense prefactor stages, vs the C oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_synthetic(d, seed=77)
+    Q = workloads.random_orthogonal(d, 21)
+    G = Q @ np.diag(m.omega * (1.0 + 0.3 * np.cos(np.arange(d)))) @ Q.T
+    G = 0.5 * (G + G.T)
+    n, nt = 131, 9
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(600 + d))
+    dt, _ = workloads.test_time_grid()
+    opot = oracle.Potential.morse(m.omega, m.chi, m.nac)
+    ref = oracle.run(opot, oracle.Consts(G, G, G, m.q0, m.p0), zi, probi, dt, nt + 1, m.en_zpt)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    a0, i0 = pr.autocorrelation(m.en_zpt), pr.ic_correlation(pot, m.en_zpt)
+    a, i = pr.propagate(pot, dt, nt, m.en_zpt)
+    assert pr.kernel_name().startswith("k_rk4_stream+k_rmult+")
+    assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    assert relerr(pr.y.cpu().numpy(), ref['y']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
+
+
 @pytest.mark.parametrize("name", ["hk_as24_rot", "hk_as60_rot"])
 def test_rotated_models_run_on_the_stream_pipeline(name, cuda_device):
     """per-trajectory dense Hessians (Q diag(h) Q^T formed by k_expand_hessian) + dense width matrices: the reference's own
