@@ -110,6 +110,28 @@ def methylium_case(name, propagators, potentials, readers, units, ntraj, nt, kin
     _propagate(name, propagators, pot, fields, G0, G0, G0, x0, np.zeros_like(x0), ntraj, dt, nt, en_zpt, kind=kind, **kw)
 
 
+def rates_case(name):
+    """k_IC(E) by the reference's rates.rate_from_correlation (rates.py:20-82) with its gaussian and lorentzian lineshapes
+    (broadening.py) on the IC correlation function of the hk_as5_chi002 fixture; row f4 of SURVEY section 8"""
+    import importlib
+    rates = importlib.import_module("semiclassical.rates")
+    broadening = importlib.import_module("semiclassical.broadening")
+    units = importlib.import_module("semiclassical.units")
+    g = np.load(os.path.join(GOLDEN, "hk_as5_chi002.npz"))
+    nt = int(g['nt'])
+    times = np.linspace(0.0, nt * float(g['dt']), nt)              # the driver's grid (cli.py:312-313)
+    corr = g['ic_correlation']
+    sigma = 0.01 / np.sqrt(2.0 * np.log(2.0)) / units.hartree_to_ev
+    gamma = 1.0e-3 / units.hartree_to_ev
+    e1, r1 = rates.rate_from_correlation(times, corr, broadening.gaussian(sigma))
+    e2, r2 = rates.rate_from_correlation(times, corr, broadening.lorentzian(gamma))
+    path = os.path.join(GOLDEN, name + ".npz")
+    np.savez_compressed(path, times=times, correlation=corr, sigma=sigma, gamma=gamma, energies=e1, rate_gaussian=r1,
+                        energies_l=e2, rate_lorentzian=r2)
+    print(f"{name:28s} nt={nt} max|k(E)| gaussian {np.abs(r1).max():.3e} lorentzian {np.abs(r2).max():.3e} "
+          f"{os.path.getsize(path)/1024:.0f} KB")
+
+
 def c2_full_size_case(name, propagators, potentials, ntraj=10000, seed=2002):
     """BASELINE configs[1] at its full size: AS 5 modes (chi = 0.02), Walton-Manolopoulos alpha = beta = 500, 10^4 trajectories,
     time grid of tests/test_propagators.py:378-382.  The ensemble is NOT stored: it is drawn by oracle.sample_ensemble from a
@@ -380,6 +402,8 @@ def main():
         Gi = np.array([[5.0]])
         diag_case("diag_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 500,
                   float(times[1] - times[0]), nt, 0.5, 128, seed=4, xspread=3.0)
+    if want("rates_as5"):
+        rates_case("rates_as5")
     if want("c2_wm_as5_n10000"):
         c2_full_size_case("c2_wm_as5_n10000", propagators, potentials)
     if want("hk_gdml_coumarin"):
