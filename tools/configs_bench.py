@@ -46,5 +46,5 @@ d = len(pos)
 masses = np.full(d, 12.0 * 1822.888486192)
 potg = potentials.MolecularGDMLPotential.from_arrays(model, masses, 1.0e-3 * np.ones(d))
 Gg = np.diag(np.full(d, 20.0))
-run("C5 sGDML N=17 HK (stage interface)", propagators.HermanKlukPropagator(T(Gg), T(Gg), device=dev), potg, pos, np.zeros(d), Gg, 20000, 0.5, 5,
+run("C5 sGDML N=17 HK", propagators.HermanKlukPropagator(T(Gg), T(Gg), device=dev), potg, pos, np.zeros(d), Gg, 20000, 0.5, 5,
     0.0, reps=2)
