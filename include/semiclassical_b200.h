@@ -151,6 +151,11 @@ int sc_engine_stage_apply(sc_engine *eng, int stage, double dt, const double *ma
 int sc_engine_stage_finish(sc_engine *eng, double dt, void *stream);
 /* correlations with caller-supplied NAC data: n1 = -tau1/m as constant vector (d) on the host */
 int sc_engine_correlations_n1(sc_engine *eng, const double *n1_host, double *out_host, void *stream);
+/* the same two sums for potentials whose couplings depend on the position (propagators.py:868-909 in full generality;
+ * Herman-Kluk): n1Q_dev, n1q_dev (d, n) = -hbar^2 tau1 / m at the current and at the initial positions
+ * (potential.derivative_coupling_1st), n2Q_dev, n2q_dev (n) = -hbar^2/2 sum_k tau2_k / m_k (derivative_coupling_2nd) */
+int sc_engine_correlations_general(sc_engine *eng, const double *n1Q_dev, const double *n1q_dev, const double *n2Q_dev,
+                                   const double *n2q_dev, double *out_host, void *stream);
 
 /* accessors (propagators.py:914-948): state in the reference's layout, prefactor and branch signs */
 int sc_engine_get_state(sc_engine *eng, double *y_dev, void *stream);            /* (2d+4d^2+1, n) */

@@ -110,6 +110,38 @@ def methylium_case(name, propagators, potentials, readers, units, ntraj, nt, kin
     _propagate(name, propagators, pot, fields, G0, G0, G0, x0, np.zeros_like(x0), ntraj, dt, nt, en_zpt, kind=kind, **kw)
 
 
+class PositionDependentNAC(object):
+    """potential protocol wrapper whose couplings depend on the position: tau1(r) = nac (1 + 0.2 r), tau2(r) = 0.05 nac r
+    (elementwise) -- exercises propagators.py:868-909 in full generality; no shipped potential does"""
+    def __init__(self, inner, nac):
+        self.inner, self.nac = inner, nac
+
+    def dimensions(self): return self.inner.dimensions()
+    def masses(self): return self.inner.masses()
+    def harmonic_approximation(self, r): return self.inner.harmonic_approximation(r)
+    def derivative_coupling_1st(self, r): return self.nac.to(r.device).unsqueeze(1) * (1.0 + 0.2 * r)
+    def derivative_coupling_2nd(self, r): return 0.05 * self.nac.to(r.device).unsqueeze(1) * r
+
+
+def posnac_case(name, propagators, potentials, ntraj=300, nt=30, rotate_seed=None):
+    model = workloads.as_5modes(0.02)
+    dt, _ = workloads.test_time_grid()
+    inner = potentials.MorsePotential(T(model.omega.copy()), T(model.chi.copy()), T(model.nac.copy()))
+    G = np.diag(model.omega)
+    q0, p0 = model.q0, model.p0
+    fields = dict(potential="morse", omega=model.omega, chi=model.chi, nac=model.nac, posnac=1)
+    nac = T(model.nac.copy())
+    if rotate_seed is not None:
+        Q = workloads.random_orthogonal(model.dim, rotate_seed)
+        inner = refrun.RotatedPotential(inner, T(Q))
+        G = Q @ G @ Q.T
+        G = 0.5 * (G + G.T)
+        q0, p0 = Q @ q0, Q @ p0
+        nac = T(Q @ model.nac)
+        fields.update(potential="rotated_morse", Q=Q)
+    _propagate(name, propagators, PositionDependentNAC(inner, nac), fields, G, G, G, q0, p0, ntraj, dt, nt, model.en_zpt, seed=9)
+
+
 def rates_case(name):
     """k_IC(E) by the reference's rates.rate_from_correlation (rates.py:20-82) with its gaussian and lorentzian lineshapes
     (broadening.py) on the IC correlation function of the hk_as5_chi002 fixture; row f4 of SURVEY section 8"""
@@ -402,6 +434,10 @@ def main():
         Gi = np.array([[5.0]])
         diag_case("diag_1d", propagators, pot, fields, Gi, Gi, np.array([[1.0]]), np.array([7.3]), np.array([0.0]), 500,
                   float(times[1] - times[0]), nt, 0.5, 128, seed=4, xspread=3.0)
+    if want("hk_as5_posnac"):
+        posnac_case("hk_as5_posnac", propagators, potentials)
+    if want("hk_as5_rot_posnac"):
+        posnac_case("hk_as5_rot_posnac", propagators, potentials, ntraj=200, nt=20, rotate_seed=7)
     if want("rates_as5"):
         rates_case("rates_as5")
     if want("c2_wm_as5_n10000"):

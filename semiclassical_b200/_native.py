@@ -104,6 +104,7 @@ _SIGNATURES = {
     "sc_engine_step_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp]),
     "sc_engine_correlations": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "sc_engine_correlations_n1": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "sc_engine_correlations_general": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sc_engine_stage_positions": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, _vp, _vp]),
     "sc_engine_stage_apply": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sc_engine_stage_finish": (ctypes.c_int, [_vp, ctypes.c_double, _vp]),

@@ -113,6 +113,7 @@ struct sc_engine {
   std::vector<double> hR, hG0iG, hp0;  // host: R = G0 iGi0 Gi, G0 iGi0, p0
   const double *oiA = nullptr, *oiB = nullptr, *oiC = nullptr;
   double *d_wR = nullptr, *d_wG = nullptr;
+  const double *d_R = nullptr, *d_G0iG = nullptr;   // R = G0 iGi0 Gi and G0 iGi0 on the device (position-dependent NAC read-out)
   const sc_potential *nac_pot = nullptr;
   std::vector<double> nac_cache;
   double *partials = nullptr;
@@ -455,6 +456,8 @@ extern "C" int sc_engine_create(sc_engine **out, const sc_engine_config *cfg) {
       e->hR[i * d + j] = s;
     }
   e->hp0.assign(cfg->p0, cfg->p0 + d);
+  UP(e->d_R, e->hR.data(), dd);
+  UP(e->d_G0iG, e->hG0iG.data(), dd);
   {
     cudaError_t ce = e->pool.alloc((size_t)d, &e->d_wR);
     if (ce == cudaSuccess) ce = e->pool.alloc((size_t)d, &e->d_wG);
@@ -1182,6 +1185,29 @@ extern "C" int sc_engine_correlations_n1(sc_engine *e, const double *n1_host, do
   none.n1 = nullptr;
   // the WM kernel reads n1 from device memory: stage it through the engine's cache
   return correlations_impl(e, none, n1_host, out_host, static_cast<cudaStream_t>(stream));
+}
+
+// autocorrelation / ic_correlation at the current time with POSITION-DEPENDENT couplings tau1(r), tau2(r)
+// (propagators.py:868-909 in full generality; Herman-Kluk).  n1Q_dev, n1q_dev: (d, n) = -hbar^2 tau1 / m at the current and at
+// the initial positions; n2Q_dev, n2q_dev: (n) = -hbar^2 / 2 sum_k tau2_k / m_k.  out_host: 4 doubles (no phase factor).
+extern "C" int sc_engine_correlations_general(sc_engine *e, const double *n1Q_dev, const double *n1q_dev, const double *n2Q_dev,
+                                              const double *n2q_dev, double *out_host, void *stream) {
+  if (!e || e->dev.n < 1 || !n1Q_dev || !n1q_dev || !n2Q_dev || !n2q_dev || !out_host) return fail(SC_ERR_INVALID, "null argument / no ensemble");
+  if (e->cfg.wm) return fail(SC_ERR_UNSUPPORTED, "position-dependent couplings: Herman-Kluk propagator only");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = e->dev.n;
+  int grid = std::min((n + 7) / 8, e->sm_count * 8);
+  if (grid < 1) grid = 1;
+  if (int rc = ensure_partials(e, (size_t)grid * 5, st)) return rc;
+  if (int rc = ensure_corr(e, 1, st)) return rc;
+  k_corr_general<<<grid, 256, 0, st>>>(e->dev, e->d_R, e->d_G0iG, n1Q_dev, n1q_dev, n2Q_dev, n2q_dev, e->partials);
+  CU(cudaGetLastError());
+  k_reduce_partials<<<1, 160, 0, st>>>(e->partials, grid, 1, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, e->corr_dev);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_host, e->corr_dev, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  e->launches += 2;
+  return SC_OK;
 }
 
 extern "C" int sc_engine_get_state(sc_engine *e, double *y, void *stream) {

@@ -1050,6 +1050,93 @@ k_corr_now(EngDev E, double *__restrict__ partials) {
 // separable models too: their diagonal stage Hessians are expanded to full matrices (the kernel multiplies whatever it is
 // given).  With diagonal full-rank widths and d > 32 the structured pipeline of sc_chunk.cuh is faster and is preferred by
 // the dispatcher unless the dense engine is asked for (option dense_engine)
+// contributions of the CURRENT state with POSITION-DEPENDENT non-adiabatic couplings (propagators.py:868-909 in full
+// generality): n1Q, n1q (d, n) = -hbar^2 tau1 / m at the current / initial positions, n2Q, n2q (n) = -hbar^2/2 sum_k tau2_k / m_k;
+//   nacQ = n2Q + (q0 - Q) R n1Q - i PI . n1Q,   PI = p0 + G0 iGi0 (P - p0)
+//   nacq = n2q + (q0 - q) R n1q + i pi . n1q,   pi = p0 + G0 iGi0 (p - p0),      R = G0 iGi0 Gi
+// One warp per trajectory, per-block partial rows (C_auto re, im, k_ic re, im, 0).
+__global__ void __launch_bounds__(256)
+k_corr_general(EngDev E, const double *__restrict__ R, const double *__restrict__ G0iG, const double *__restrict__ n1Q,
+               const double *__restrict__ n1q, const double *__restrict__ n2Q, const double *__restrict__ n2q,
+               double *__restrict__ partials) {
+  __shared__ double sh[8][6 * SC_MAX_DIM];
+  __shared__ double red[8][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, d = E.d, n = E.n;
+  double *dQv = sh[warp], *dPv = dQv + d, *dqv = dPv + d, *dpv = dqv + d, *nQ = dpv + d, *nq = nQ + d;
+  double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int traj = blockIdx.x * 8 + warp; traj < n; traj += gridDim.x * 8) {
+    const double *rec = E.rec + (size_t)traj * E.rs;
+    const double *zt = E.zt + (size_t)traj * 2 * d;
+    __syncwarp();
+    for (int a = lane; a < d; a += 32) {
+      dQv[a] = E.q0[a] - rec[a];            // q0 - Q
+      dPv[a] = E.p0[a] - rec[d + a];        // p0 - P
+      dqv[a] = E.q0[a] - zt[a];             // q0 - q
+      dpv[a] = E.p0[a] - zt[d + a];         // p0 - p
+      nQ[a] = n1Q[(size_t)a * n + traj];
+      nq[a] = n1q[(size_t)a * n + traj];
+    }
+    __syncwarp();
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int a = lane; a < d; a += 32) {
+      const double dq = dQv[a], dpa = dPv[a];
+      if (E.diag) {
+        v[0] += -0.5 * (dq * E.otA[a] * dq + dpa * E.otB[a] * dpa);
+        v[1] += -E.p0[a] * dq + dq * E.otC[a] * dpa;
+      } else {
+        double sa = 0.0, sb = 0.0, sc_ = 0.0;
+        for (int j = 0; j < d; ++j) {
+          sa = fma(__ldg(E.otA + j * d + a), dQv[j], sa);
+          sb = fma(__ldg(E.otB + j * d + a), dPv[j], sb);
+          sc_ = fma(__ldg(E.otC + j * d + a), dQv[j], sc_);
+        }
+        v[0] += -0.5 * (dq * sa + dpa * sb);
+        v[1] += -E.p0[a] * dq + dpa * sc_;
+      }
+      // row a of R n1 and of G0 iGi0 (p0 - P): coalesced over the lanes through the transposed access (column a)
+      double rQ = 0.0, rq = 0.0, gP = 0.0, gp = 0.0;
+      for (int j = 0; j < d; ++j) {
+        const double r = __ldg(R + (size_t)a * d + j), g = __ldg(G0iG + (size_t)a * d + j);
+        rQ = fma(r, nQ[j], rQ);
+        rq = fma(r, nq[j], rq);
+        gP = fma(g, dPv[j], gP);
+        gp = fma(g, dpv[j], gp);
+      }
+      v[2] += dq * rQ;                                   // (q0 - Q) R n1Q
+      v[3] += (E.p0[a] - gP) * nQ[a];                    // PI . n1Q,  PI_a = p0_a - [G0 iGi0 (p0 - P)]_a
+      v[4] += dqv[a] * rq;                               // (q0 - q) R n1q
+      v[5] += (E.p0[a] - gp) * nq[a];                    // pi . n1q
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
+    if (lane == 0) {
+      const double2 c = E.c[traj], wvi = E.wvi[traj];
+      const double sg = E.sign[traj];
+      const double2 e = cexp(v[0], rec[2 * d] - v[1]);
+      double2 cq = cmul(make_double2(E.ot_fac * e.x, E.ot_fac * e.y), wvi);
+      cq = cmul(cq, make_double2(sg * c.x, sg * c.y));
+      const double2 nacQ = make_double2(n2Q[traj] + v[2], -v[3]);
+      const double2 nacq = make_double2(n2q[traj] + v[4], v[5]);
+      const double2 k = cmul(cmul(nacQ, nacq), cq);
+      acc4[0] += cq.x; acc4[1] += cq.y; acc4[2] += k.x; acc4[3] += k.y;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[warp][i] = acc4[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double s = 0.0;
+    if (threadIdx.x < 4)
+      for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * 5 + threadIdx.x] = s;
+  }
+}
+
 static bool stream_supported(const EngDev &E, const PotDev &P) {
   if (E.d < 17 || E.d > SC_MAX_DIM) return false;
   if (P.type == POT_HARMONIC) return true;

@@ -398,23 +398,48 @@ class HermanKlukPropagator(object):
                     _native.check(_native.lib().sc_engine_correlations(self._engine, handle, out.ctypes.data, self._stream()))
                 else:
                     n1 = self._constant_n1(potential)
-                    _native.check(_native.lib().sc_engine_correlations_n1(self._engine, n1.ctypes.data, out.ctypes.data, self._stream()))
+                    if n1 is not None:
+                        _native.check(_native.lib().sc_engine_correlations_n1(self._engine, n1.ctypes.data, out.ctypes.data, self._stream()))
+                    else:
+                        self._correlations_general(potential, out)
         res = (out[0] + 1j * out[1], out[2] + 1j * out[3])
         if potential is not None:
             self._corr_cache = (potential, res[0], res[1])
         return res
 
     def _constant_n1(self, potential):
-        """n1 = -hbar^2 tau1/m for potentials whose NAC vector is constant (all shipped ones, Condon approximation)"""
+        """n1 = -hbar^2 tau1/m for potentials whose NAC vector is constant and whose second-order coupling vanishes (all shipped
+        ones, Condon approximation); None if the couplings depend on the position (-> _correlations_general)"""
         q, _ = self.current_positions_and_momenta()
-        tau1 = potential.derivative_coupling_1st(q[:, :min(2, self.ntraj)])
-        tau2 = potential.derivative_coupling_2nd(q[:, :min(2, self.ntraj)])
-        if tau1.shape[1] > 1 and not torch.equal(tau1[:, 0], tau1[:, 1]):
-            raise NotImplementedError("position-dependent non-adiabatic coupling vectors are not supported")
-        if float(abs(tau2).max()) != 0.0:
-            raise NotImplementedError("second-order derivative couplings are not supported")
+        probe = q[:, :min(3, self.ntraj)]
+        tau1 = potential.derivative_coupling_1st(probe)
+        tau2 = potential.derivative_coupling_2nd(probe)
+        varies = tau1.shape[1] > 1 and not all(torch.equal(tau1[:, 0], tau1[:, k]) for k in range(1, tau1.shape[1]))
+        if not varies and self.ntraj > 1:
+            # a second probe at the initial positions: constant means constant everywhere the ensemble has been
+            tau1i = potential.derivative_coupling_1st(self.zi[:self.dim, :1].contiguous())
+            varies = not torch.equal(tau1i[:, 0], tau1[:, 0])
+        if varies or float(abs(tau2).max()) != 0.0:
+            return None
         masses = potential.masses().to(self.device)
         return np.ascontiguousarray((-hbar**2 * tau1[:, 0] / masses).detach().cpu().numpy())
+
+    def _correlations_general(self, potential, out):
+        """position-dependent couplings (propagators.py:868-909 in full generality): the potential object evaluates tau1, tau2 at
+        the initial and at the current positions, the engine's kernel does the rest (k_corr_general)"""
+        if self._wm:
+            raise NotImplementedError("position-dependent non-adiabatic couplings: Herman-Kluk propagator only")
+        d = self.dim
+        Q, _ = self.current_positions_and_momenta()
+        Q = Q.contiguous()
+        q = self.zi[:d].contiguous()
+        im = (1.0 / potential.masses().to(device=self.device, dtype=torch.float64)).unsqueeze(1)
+        n1Q = (-hbar**2 * im * potential.derivative_coupling_1st(Q)).to(torch.float64).contiguous()
+        n1q = (-hbar**2 * im * potential.derivative_coupling_1st(q)).to(torch.float64).contiguous()
+        n2Q = (-0.5 * hbar**2 * (im * potential.derivative_coupling_2nd(Q)).sum(dim=0)).to(torch.float64).contiguous()
+        n2q = (-0.5 * hbar**2 * (im * potential.derivative_coupling_2nd(q)).sum(dim=0)).to(torch.float64).contiguous()
+        _native.check(_native.lib().sc_engine_correlations_general(self._engine, n1Q.data_ptr(), n1q.data_ptr(), n2Q.data_ptr(),
+                                                                   n2q.data_ptr(), out.ctypes.data, self._stream()))
 
     def autocorrelation(self, energy0_es=0.0):
         """e^{i t E0/hbar} <phi(0)|phi(t)> at the current time step (propagators.py:809-843)"""

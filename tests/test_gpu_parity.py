@@ -315,6 +315,35 @@ class _PythonPotential(object):
         return self.inner.derivative_coupling_2nd(r)
 
 
+class _PositionDependentNAC(_PythonPotential):
+    """tau1(r) = nac (1 + 0.2 r), tau2(r) = 0.05 nac r -- the wrapper the fixtures hk_as5*_posnac were generated with"""
+    def __init__(self, inner, nac):
+        super().__init__(inner)
+        self.nac = nac
+
+    def derivative_coupling_1st(self, r):
+        return self.nac.to(r.device).unsqueeze(1) * (1.0 + 0.2 * r)
+
+    def derivative_coupling_2nd(self, r):
+        return 0.05 * self.nac.to(r.device).unsqueeze(1) * r
+
+
+@pytest.mark.parametrize("name", ["hk_as5_posnac", "hk_as5_rot_posnac"])
+def test_position_dependent_couplings_match_reference(name, cuda_device):
+    """ic_correlation with couplings that depend on the position (propagators.py:868-909 in full generality, no shipped
+    potential has them): the potential object supplies tau1, tau2 at the initial and current positions, k_corr_general the
+    rest; diagonal and dense (rotated) width matrices, against the reference's golden"""
+    g = helpers.load_golden(name)
+    inner = helpers.potential_from_golden(g)
+    nac = T(g['Q'] @ g['nac']) if 'Q' in g.files else T(g['nac'])
+    pot = _PositionDependentNAC(inner, nac)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    nt = int(g['nt'])
+    auto, ic = run_loop(pr, pot, float(g['dt']), nt, float(g['energy0_es']))
+    assert relerr(auto, g['autocorrelation']) < TOL
+    assert relerr(ic, g['ic_correlation']) < TOL
+
+
 @pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium", "hk_as24_rot", "wm_as5_rot"])
 def test_python_potential_through_stage_interface(name, cuda_device):
     g = helpers.load_golden(name)
