@@ -85,6 +85,14 @@ int main(int argc, char **argv) {
     ms = run_mma<2>(dA, dr, nmat, ddet, 2); check("DMMA occ2", ms);
     cudaMemset(ddet, 0, sizeof(double2) * nmat);
     ms = run_mma<1>(dA, dr, nmat, ddet, 1); check("DMMA occ1", ms);
+    // warps per matrix at 3 matrices per SM, and occupancy scaling with 2 warps per matrix (small d': more matrices fit)
+    ms = run_mma<3, 2>(dA, dr, nmat, ddet, 3); check("DMMA 2 warps occ3", ms);
+    ms = run_mma<3, 1>(dA, dr, nmat, ddet, 3); check("DMMA 1 warp occ3", ms);
+    ms = run_mma<3, 8>(dA, dr, nmat, ddet, 3); check("DMMA 8 warps occ3", ms);
+    ms = run_mma<1, 2>(dA, dr, nmat, ddet, 1); check("DMMA 2 warps occ1", ms);
+    ms = run_mma<2, 2>(dA, dr, nmat, ddet, 2); check("DMMA 2 warps occ2", ms);
+    if (lum_smem_bytes(dr) * 4 + 4096 < 227 * 1024) { ms = run_mma<4, 2>(dA, dr, nmat, ddet, 4); check("DMMA 2 warps occ4", ms); }
+    if (lum_smem_bytes(dr) * 5 + 5120 < 227 * 1024) { ms = run_mma<5, 2>(dA, dr, nmat, ddet, 5); check("DMMA 2 warps occ5", ms); }
     cudaMemset(ddet, 0, sizeof(double2) * nmat);
     ms = run_mma<3, 2>(dA, dr, nmat, ddet, 3); check("DMMA 2 warps occ3", ms);
     cudaMemset(ddet, 0, sizeof(double2) * nmat);
