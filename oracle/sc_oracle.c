@@ -530,6 +530,10 @@ static void hk_contrib(const sc_oracle_potential *P, const sc_oracle_consts *K, 
   *kic = nacQ * nacq * cq * w;
 }
 
+/* optional export of the pieces the WM wavefunction diagnostics need (propagators.py:1339-1342): when non-NULL, wm_prefactor
+ * writes [CQQ (d^2) | CqQ (d^2) | PIq (d) | PIQ (d) | eps] of the trajectory there */
+static __thread cplx *g_wm_export = NULL;
+
 /* WM prefactor pieces for one trajectory (propagators.py:1155-1389) */
 static void wm_prefactor(const sc_oracle_consts *K, traj_t *T, const double *zi, cplx *w) {
   const int d = K->d, dr = K->dr, d2 = d * d, D2 = 2 * d, R2 = 2 * dr;
@@ -639,6 +643,13 @@ static void wm_prefactor(const sc_oracle_consts *K, traj_t *T, const double *zi,
     PIQ[i] = pit[i] + s2;     /* eqn 73 */
   }
   const cplx eps = 0.5 * cquad(iA, b0, b0, D2) - 0.5 * cquad(iGc, v2, v2, d); /* eqn 74 */
+  if (g_wm_export) {
+    memcpy(g_wm_export, CQQ, sizeof(cplx) * d2);
+    memcpy(g_wm_export + d2, CqQ, sizeof(cplx) * d2);
+    memcpy(g_wm_export + 2 * d2, PIq, sizeof(cplx) * d);
+    memcpy(g_wm_export + 2 * d2 + d, PIQ, sizeof(cplx) * d);
+    g_wm_export[2 * d2 + 2 * d] = eps;
+  }
   /* det(A' / (2 sqrt(alpha beta))) */
   const double sc = 2.0 * sqrt(K->alpha * K->beta);
   for (int i = 0; i < R2 * R2; ++i) t2[i] = Ap[i] / sc;
@@ -800,6 +811,33 @@ int sc_oracle_run(const sc_oracle_potential *P, const sc_oracle_consts *K, int w
   }
   free(acc); free(wmbuf); free(T); free(Z); free(Y);
   return rc;
+}
+
+/*
+ * Pieces of the Walton-Manolopoulos wavefunction diagnostics (propagators.py:1391-1575) for a given state y (ylen, n) of an
+ * ensemble zi (2d, n): out (n, 2 d^2 + 2 d + 2) complex = [CQQ | CqQ | PIq | PIQ | eps | detA] per trajectory, recomputed by
+ * wm_prefactor (no branch tracking: the trackers of the run are passed separately to the numpy restatement).
+ */
+int sc_oracle_wm_diag(const sc_oracle_consts *K, int n, const double *y_in, const double *zi, cplx *out) {
+  const int d = K->d, L = ylen(d), d2 = d * d, D2 = 2 * d;
+  const size_t wsz = (size_t)16 * D2 * D2 + 64 * d + 64, stride = 2 * (size_t)d2 + 2 * d + 2;
+  cplx *w = (cplx *)malloc(sizeof(cplx) * wsz), *buf = (cplx *)calloc(3 * d2 + 2 * d, sizeof(cplx));
+  double *y = (double *)malloc(sizeof(double) * L), *z = (double *)malloc(sizeof(double) * 2 * d);
+  for (int t = 0; t < n; ++t) {
+    traj_t T;
+    memset(&T, 0, sizeof(T));
+    for (int k = 0; k < L; ++k) y[k] = y_in[(size_t)k * n + t];
+    for (int k = 0; k < 2 * d; ++k) z[k] = zi[(size_t)k * n + t];
+    T.y = y;
+    T.Rqq = buf; T.RQQ = buf + d2; T.RqQ = buf + 2 * d2; T.Pq = buf + 3 * d2; T.PQ = buf + 3 * d2 + d;
+    hk_prefactor(K, &T, w);
+    g_wm_export = out + (size_t)t * stride;
+    wm_prefactor(K, &T, z, w);
+    g_wm_export = NULL;
+    out[(size_t)t * stride + stride - 1] = T.detA;
+  }
+  free(w); free(buf); free(y); free(z);
+  return 0;
 }
 
 int sc_oracle_num_threads(void) {

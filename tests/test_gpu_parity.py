@@ -404,6 +404,30 @@ def test_wavefunction_diagnostics_match_reference(name, cuda_device):
     assert relerr(phi, g['wavefunction']) < TOL
 
 
+def test_wm_diagnostics_against_oracle_on_fresh_ensemble(cuda_device):
+    """Walton-Manolopoulos coefficients / wavefunction / norm on an ensemble that is in no fixture (n = 257: ragged for every
+    kernel shape) vs the oracle's restatement of propagators.py:1391-1575"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_5modes(0.02)
+    G = np.diag(m.omega)
+    n, nt = 257, 7
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(4711))
+    dt, _ = workloads.test_time_grid()
+    consts = oracle.Consts(G, G, G, m.q0, m.p0, 300.0, 300.0)
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), consts, zi, probi, dt, nt, m.en_zpt, wm=True)
+    pc = oracle.wm_diag_pieces(consts, ref['y'], zi)
+    v = oracle.wm_coefficients(consts, zi, probi, ref['y'], ref['c'], ref['signs'][0], ref['signs'][1], pc)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.WaltonManolopoulosPropagator(T(G), T(G), 300.0, 300.0, device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    pr.propagate(pot, dt, nt, m.en_zpt)
+    assert relerr(pr.coefficients().cpu().numpy(), v) < TOL
+    x = m.q0[:, None] + 0.05 * np.random.default_rng(6).standard_normal((5, 23))
+    assert relerr(pr.wavefunction(T(x)), oracle.wm_wavefunction(consts, zi, ref['y'], v, pc, x)) < TOL
+    assert abs(pr.norm() / oracle.wm_norm(consts, zi, ref['y'], v, pc) - 1.0) < TOL
+
+
 def test_sharded_norm_blocks_add_up(cuda_device):
     """norm() of a sharded ensemble (propagators.py:734-782 is all pairs of the GLOBAL ensemble): two shards on one device,
     the four (n_a x n_b) blocks through sc_engine_norm_pack / sc_engine_norm_block add up to the reference's norm"""
