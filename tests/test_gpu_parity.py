@@ -344,8 +344,10 @@ def test_position_dependent_couplings_match_reference(name, cuda_device):
     assert relerr(ic, g['ic_correlation']) < TOL
 
 
-@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium", "hk_as24_rot", "wm_as5_rot"])
+@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium", "hk_as24_rot", "wm_as5_rot", "hk_as60", "hk_as60_rot"])
 def test_python_potential_through_stage_interface(name, cuda_device):
+    """any object with the potential protocol drives the RK4 stages; d >= 17 runs on the dense column pipeline (the
+    caller's (d, d, n) Hessians become the stream images of the four stages), smaller d on the DFMA stage kernel"""
     g = helpers.load_golden(name)
     pot = _PythonPotential(helpers.potential_from_golden(g))
     pr = helpers.propagator_from_golden(g, cuda_device)
@@ -353,6 +355,35 @@ def test_python_potential_through_stage_interface(name, cuda_device):
     auto, ic = run_loop(pr, pot, float(g['dt']), nt, float(g['energy0_es']))
     assert relerr(auto, g['autocorrelation'][:nt]) < TOL
     assert relerr(ic, g['ic_correlation'][:nt]) < TOL
+    if nt == int(g['nt']):
+        nk = g['y_final'].shape[1]
+        assert relerr(pr.y[:, :nk].cpu().numpy(), g['y_final']) < TOL
+        assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
+
+
+def test_python_potential_at_d72(cuda_device):
+    """a user potential object for a 24-atom harmonic molecule (d = 72, d' = 66: beyond the DFMA stage kernel's shared memory)
+    through the stage interface on the dense column pipeline, vs the C oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    d = 72
+    m = workloads.harmonic_molecule_synthetic(d)
+    G = m['Gamma_0']
+    n, nt = 37, 5
+    zi, probi = oracle.sample_ensemble(G, G, m['q0'], m['p0'], n, np.random.default_rng(72))
+    dt, _ = workloads.test_time_grid()
+    opot = oracle.Potential.harmonic(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    ref = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt, m['en_zpt'])
+    pot = _PythonPotential(potentials.MolecularHarmonicPotential.from_arrays(m['pos0'], m['energy0'], m['grad0'], m['hess0'],
+                                                                             m['masses'], m['nac']))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m['q0']), T(m['p0']), T(G), T(zi), T(probi))
+    auto, ic = run_loop(pr, pot, dt, nt, m['en_zpt'])
+    assert pr.kernel_name().startswith("stage interface: k_rk4_stream")
+    assert relerr(auto, ref['autocorrelation']) < TOL
+    assert relerr(ic, ref['ic_correlation']) < TOL
+    assert relerr(pr.y.cpu().numpy(), ref['y']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
 
 
 # ------------------------------------------------------------------ column-chunked headline path
