@@ -717,6 +717,47 @@ def test_dense_engine_option_on_separable_model(d, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
+@pytest.mark.parametrize("which", ["as_structured", "as_dense_engine", "harmonic_dense"])
+def test_long_horizon_d60(which, cuda_device):
+    """the reference's full time grid (100 steps of tests/test_propagators.py:378-382) at d = 60 on both column pipelines:
+    the 1e-9 bar and the bit-identical branch signs must hold over the whole horizon, not only over the 25 steps of the
+    hk_as60* fixtures (fused launches of 33 steps: several passes over the state, branch flips included)"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    dt, nt = workloads.test_time_grid()
+    n = 40
+    if which == "harmonic_dense":
+        m = workloads.harmonic_molecule_synthetic(60)
+        G, q0, p0, e0 = m['Gamma_0'], m['q0'], m['p0'], m['en_zpt']
+        opot = oracle.Potential.harmonic(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+        pot = potentials.MolecularHarmonicPotential.from_arrays(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    else:
+        m = workloads.as_synthetic(60)
+        G, q0, p0, e0 = np.diag(m.omega), m.q0, m.p0, m.en_zpt
+        opot = oracle.Potential.morse(m.omega, m.chi, m.nac)
+        pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    zi, probi = oracle.sample_ensemble(G, G, q0, p0, n, np.random.default_rng(900))
+    ref = oracle.run(opot, oracle.Consts(G, G, G, q0, p0), zi, probi, dt, nt, e0)
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(q0), T(p0), T(G), T(zi), T(probi))
+    if which == "as_dense_engine":
+        pr.set_option("dense_engine", 1)
+    auto, ic = [pr.autocorrelation(e0)], [pr.ic_correlation(pot, e0)]
+    for k0 in range(0, nt - 1, 33):
+        a, i = pr.propagate(pot, dt, min(33, nt - 1 - k0), e0)
+        auto.extend(a)
+        ic.extend(i)
+    expected = {"as_structured": "k_rk4_wcols", "as_dense_engine": "k_rk4_stream+k_lu", "harmonic_dense": "k_rk4_stream+k_rmult"}[which]
+    assert pr.kernel_name().startswith(expected)
+    assert relerr(auto, ref['autocorrelation']) < TOL
+    assert relerr(ic, ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    assert relerr(pr.y.cpu().numpy(), ref['y']) < TOL
+    assert relerr(pr.c.cpu().numpy(), ref['c']) < TOL
+    signs = pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy()
+    assert np.array_equal(signs, ref['signs'][0])
+
+
 # ------------------------------------------------------------------ BASELINE size: size-independent properties
 def test_full_size_properties_c4(cuda_device):
     """configs[3] at its full single-GPU size (10^6 trajectories, 60 modes, ~116 GB of state) where no oracle run is
