@@ -13,6 +13,7 @@
 
 #include "../../include/semiclassical_b200.h"
 #include "sc_kernels.cuh"
+#include "sc_small.cuh"
 #include "sc_mma.cuh"
 #include "sc_chunk.cuh"
 #include "sc_stream.cuh"
@@ -895,6 +896,21 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
     if (mode == MODE_CORR) return run_corr_now(e, out_dev, st);
     return fail(SC_ERR_UNSUPPORTED, "no fused step kernel for this potential at d = %d; use the stage interface", e->dev.d);
   }
+  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_SMALL") && small_supported(e->dev, P)) {
+    // register-resident column kernel for the small systems (sc_small.cuh); one partial row per warp and step
+    int nwarps = 0;
+    CU(launch_small(e->sm_count, e->dev, P, h, nsteps, nullptr, nwarps, true, st));
+    const size_t need = (size_t)nwarps * nsteps * 5;
+    if (int rc = ensure_partials(e, need, st)) return rc;
+    CU(cudaMemsetAsync(e->partials, 0, sizeof(double) * need, st));
+    CU(launch_small(e->sm_count, e->dev, P, h, nsteps, e->partials, nwarps, false, st));
+    e->kernel_name = "k_hk_small";
+    k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, nwarps, nsteps, 1.0 / (double)e->ntraj_norm,
+                                              1.0 / (double)e->dev.n, out_dev);
+    CU(cudaGetLastError());
+    e->launches += 2;
+    return SC_OK;
+  }
   if (int rc = plan_launch(e, pl)) return rc;
   const int nrows = (mode == MODE_STEP) ? nsteps : 1;
   const int ngroups = pl.grid * pl.groups_per_cta;
@@ -1130,7 +1146,7 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
       CU(cudaGetLastError());
       e->launches += 3;
     }
-    e->kernel_name = "k_hk_generic+k_wm_fused";
+    e->kernel_name = !strcmp(e->kernel_name, "k_hk_small") ? "k_hk_small+k_wm_fused" : "k_hk_generic+k_wm_fused";
     return SC_OK;
   }
   // larger d: the HK pipeline advances the trajectories one step at a time, the WM kernel evaluates the Filinov-smoothed

@@ -185,7 +185,7 @@ def test_c2_full_size_wm_fused_launches(cuda_device):
         a, i = pr.propagate(pot, dt, min(33, nt - 1 - k0), e0)
         auto.extend(a)
         ic.extend(i)
-    assert pr.kernel_name() == "k_hk_generic+k_wm_fused"
+    assert pr.kernel_name() == "k_hk_small+k_wm_fused"
     assert pr.launch_count() - l0 <= 3 * 5 + 3          # launches per 33 fused steps, not per step
     assert relerr(auto, g['autocorrelation']) < TOL
     assert relerr(ic, g['ic_correlation']) < TOL
