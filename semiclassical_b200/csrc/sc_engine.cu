@@ -92,6 +92,8 @@ struct WMState {
   double *n1_dev = nullptr, *scratch5 = nullptr, *partials = nullptr;
   int tpt = 32, groups = 1, grid = 1;
   size_t smem = 0;
+  double2 *gws = nullptr;           // workspace slabs in global memory when one trajectory exceeds shared memory (k_wm_global)
+  bool global_ws = false;
   // K-step fused launches: snapshots of (step, trajectory) records, per-group rows, HK rows (energies)
   void *snap = nullptr;
   size_t snap_cap = 0;
@@ -330,8 +332,14 @@ static int wm_setup(WMState &w, const sc_engine_config &cfg, DevPool &pool) {
     w.groups = 1;
   }
   w.smem = ws * w.groups;
-  if (w.smem > 227 * 1024)
-    return fail(SC_ERR_UNSUPPORTED, "Walton-Manolopoulos workspace %zu B exceeds 227 KB of shared memory (d = %d)", w.smem, d);
+  w.global_ws = false;
+  if (w.smem > 227 * 1024) {
+    // beyond about 21 modes the workspace of one trajectory does not fit in shared memory: slabs in global memory
+    w.global_ws = true;
+    w.tpt = 256;
+    w.groups = 1;
+    w.smem = 0;
+  }
   return SC_OK;
 }
 
@@ -356,10 +364,16 @@ static int wm_alloc(WMState &w, DevPool &ens, const EngDev &D, const double *q0_
   int per_sm = (int)((227 * 1024) / (w.smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2048 / (w.tpt * w.groups)) per_sm = 2048 / (w.tpt * w.groups);
+  if (w.global_ws) per_sm = 3;
   int grid = sm_count * per_sm;
   const int need = (n + w.groups - 1) / w.groups;
   if (grid > need) grid = need;
   w.grid = grid < 1 ? 1 : grid;
+  if (w.global_ws) {
+    double *slabs = nullptr;
+    CU(ens.alloc(2 * (size_t)w.L.total * w.grid, &slabs));
+    w.gws = reinterpret_cast<double2 *>(slabs);
+  }
   CU(ens.alloc((size_t)w.grid * w.groups * 4, &w.partials));
   k_wm_winv<<<(n + 255) / 256, 256, 0, st>>>(probi_dev, std::pow(2.0 * M_PI, -(double)D.d), n, winv);
   CU(cudaGetLastError());
@@ -371,7 +385,9 @@ static int wm_alloc(WMState &w, DevPool &ens, const EngDev &D, const double *q0_
 static int wm_launch(WMState &w, const EngDev &D, int mode, double inv_norm, double *out5, const double *energy_src,
                      cudaStream_t st) {
   const int threads = w.tpt * w.groups;
-  if (w.tpt == 32) {
+  if (w.global_ws) {
+    k_wm_global<256><<<w.grid, 256, 0, st>>>(D, w.dev, w.L, mode, w.partials, w.gws);
+  } else if (w.tpt == 32) {
     CU(cudaFuncSetAttribute(k_wm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
     k_wm<32><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
   } else {
@@ -1156,6 +1172,7 @@ extern "C" int sc_engine_step_dev(sc_engine *e, const sc_potential *pot, double 
     if (int rc = wm_launch(e->wm, e->dev, WM_STEP, 1.0 / (double)e->ntraj_norm, corr_dev + 5 * k, e->wm.scratch5, st)) return rc;
     e->launches += 2;
   }
+  e->kernel_name = e->wm.global_ws ? "HK step pipeline+k_wm_global" : "HK step pipeline+k_wm";
   return SC_OK;
 }
 

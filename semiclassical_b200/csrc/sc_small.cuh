@@ -24,9 +24,13 @@ struct SmallCfg {
   static constexpr int NGW = 32 / GS;                    // trajectories per warp
   static constexpr int WARPS = 4;
   static constexpr int LDH = (D + 1) & ~1;
-  static constexpr int MIN_CTAS = D <= 5 ? 3 : 2;        // register budget: 168 / 255 per thread
-  static constexpr int CTA_CONST = D * LDH + LDH;        // hess0 or Q ; 1/m
-  static constexpr int PER_GROUP = ((D * LDH + 6 * LDH + GS * 2 * DR + 8 * D) + 1) & ~1;   // doubles
+  static constexpr int MIN_CTAS = D <= 5 ? 4 : 2;        // register budget: 168 / 255 per thread
+  // per-CTA constant block (doubles): hess0 or Q | 1/m | sgt | isgt | L1 | L2 | R1 | R2 | otA | otB | otC
+  static constexpr int O_IM = D * LDH, O_SGT = O_IM + LDH, O_ISGT = O_SGT + LDH, O_L1 = O_ISGT + LDH, O_L2 = O_L1 + DR * D,
+                       O_R1 = O_L2 + DR * D, O_R2 = O_R1 + D * DR, O_OA = O_R2 + D * DR, O_OB = O_OA + D * D, O_OC = O_OB + D * D;
+  static constexpr int O_PC = (O_OC + D * D + 1) & ~1;   // per-mode constants read once per step: q0 p0 wR wG oA oB oC sgi isgi
+  static constexpr int CTA_CONST = O_PC + 9 * LDH;
+  static constexpr int PER_GROUP = ((D * LDH + 8 * LDH + GS * 2 * DR + 8 * D + 10) + 1) & ~1;   // doubles
   static constexpr size_t SMEM = sizeof(double) * (size_t)(CTA_CONST + WARPS * NGW * PER_GROUP);
 };
 
@@ -53,7 +57,8 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
   const int gbase = lane_ok ? g * GS : 0;
   double *gs = smem + Cfg::CTA_CONST + (size_t)(warp * NGW + (lane_ok ? g : 0)) * Cfg::PER_GROUP;
   double *Hs = gs, *hdv = Hs + D * LDH, *qs = hdv + LDH, *scr = qs + LDH, *scr2 = scr + LDH, *dqv = scr2 + LDH,
-         *dpv = dqv + LDH, *Tst = dpv + LDH, *red = Tst + GS * 2 * DR;
+         *dpv = dqv + LDH, *v4s = dpv + LDH, *v5s = v4s + LDH, *Tst = v5s + LDH, *red = Tst + GS * 2 * DR, *lead = red + 8 * D;
+  // lead: state of the group's leader thread (S, sign, det, sqrt(det), initial overlap), kept out of everybody's registers
   const int ptype = P.type;
   const bool separable = ptype == POT_MORSE || ptype == POT_NONHARMONIC;
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
@@ -61,16 +66,38 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
     cmat[a * LDH + k] = (ptype == POT_HARMONIC) ? P.hess0[i] : (ptype == POT_ROTATED_MORSE ? P.Q[i] : 0.0);
   }
   if (threadIdx.x < D) cim[threadIdx.x] = P.imass[threadIdx.x];
+  {
+    // the small constant tables go to shared memory once: addressed by immediates, no pointer registers in the step loop
+    double *cst = smem;
+    const int t = threadIdx.x, nt = blockDim.x;
+    for (int i = t; i < D; i += nt) {
+      double *pc = cst + Cfg::O_PC + i;
+      pc[0] = E.q0[i]; pc[LDH] = E.p0[i]; pc[2 * LDH] = E.wR[i]; pc[3 * LDH] = E.wG[i];
+      if (E.diag) {
+        pc[4 * LDH] = E.otA[i]; pc[5 * LDH] = E.otB[i]; pc[6 * LDH] = E.otC[i]; pc[7 * LDH] = E.sgi[i]; pc[8 * LDH] = E.isgi[i];
+      }
+    }
+    if (E.diag) {
+      for (int i = t; i < D; i += nt) { cst[Cfg::O_SGT + i] = E.sgt[i]; cst[Cfg::O_ISGT + i] = E.isgt[i]; }
+    } else {
+      for (int i = t; i < DR * D; i += nt) {
+        cst[Cfg::O_L1 + i] = E.L1[i]; cst[Cfg::O_L2 + i] = E.L2[i]; cst[Cfg::O_R1 + i] = E.R1[i]; cst[Cfg::O_R2 + i] = E.R2[i];
+      }
+      for (int i = t; i < D * D; i += nt) { cst[Cfg::O_OA + i] = E.otA[i]; cst[Cfg::O_OB + i] = E.otB[i]; cst[Cfg::O_OC + i] = E.otC[i]; }
+    }
+  }
   __syncthreads();
+  const double *cst = smem;
   const double *Hc = (ptype == POT_HARMONIC) ? cmat : Hs;
   const int wg = blockIdx.x * Cfg::WARPS + warp, NWG = gridDim.x * Cfg::WARPS;   // warp index, warps in the grid
   const bool modal = lane_ok && c < D;
   // per-mode constants of this thread
-  double im_c = 0, q0c = 0, p0c = 0, wrc = 0, wgc = 0, oA = 0, oB = 0, oC = 0, sgi_c = 0, isgi_c = 0, pos0c = 0, grad0c = 0;
+  double im_c = 0, pos0c = 0, grad0c = 0;
   double pa1 = 0, pa2 = 0, pa3 = 0;                       // potential parameters of mode c
+  const int cm = c < D ? c : 0;
+#define SC_PC(k) cst[Cfg::O_PC + (k) * LDH + cm]
   if (modal) {
-    im_c = P.imass[c]; q0c = E.q0[c]; p0c = E.p0[c]; wrc = E.wR[c]; wgc = E.wG[c];
-    if (E.diag) { oA = E.otA[c]; oB = E.otB[c]; oC = E.otC[c]; sgi_c = E.sgi[c]; isgi_c = E.isgi[c]; }
+    im_c = P.imass[c];
     if (ptype == POT_HARMONIC) { pos0c = P.pos0[c]; grad0c = P.grad0[c]; }
     if (ptype == POT_MORSE || ptype == POT_ROTATED_MORSE) {
       if (P.all_harmonic) pa1 = P.omega[c] * P.omega[c];
@@ -91,15 +118,18 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
       u[a] = valid ? rec[E.qps + a * W + c] : 0.0;
       v[a] = valid ? rec[E.qps + NE + a * W + c] : 0.0;
     }
-    double qa = 0, pa = 0, S = 0, sign = 1.0, v4c = 0, v5c = 0;
-    double2 c2 = make_double2(1.0, 0.0), cc = c2, wvi = make_double2(0.0, 0.0);
+    double qa = 0, pa = 0;
     if (mode_c) {
       qa = rec[c]; pa = rec[D + c];
       const double *zt = E.zt + (size_t)traj * 2 * D;
-      v4c = (q0c - zt[c]) * wrc;
-      v5c = (zt[D + c] - p0c) * wgc;
+      v4s[c] = (SC_PC(0) - zt[c]) * SC_PC(2);
+      v5s[c] = (zt[D + c] - SC_PC(1)) * SC_PC(3);
     }
-    if (valid && c == 0) { S = rec[2 * D]; c2 = E.c2[traj]; cc = E.c[traj]; sign = E.sign[traj]; wvi = E.wvi[traj]; }
+    if (valid && c == 0) {
+      const double2 c2 = E.c2[traj], cc = E.c[traj], wvi = E.wvi[traj];
+      lead[0] = rec[2 * D]; lead[1] = E.sign[traj]; lead[2] = c2.x; lead[3] = c2.y; lead[4] = cc.x; lead[5] = cc.y;
+      lead[6] = wvi.x; lead[7] = wvi.y;
+    }
 
     for (int step = 0; step < nsteps; ++step) {
       // ================= one classical RK4 step =================
@@ -107,7 +137,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
 #pragma unroll
       for (int a = 0; a < D; ++a) { us[a] = u[a]; R1[a] = 0.0; R2[a] = 0.0; }
       double qsa = qa, psa = pa, accq = 0, accp = 0, accS = 0, e4 = 0;
-#pragma unroll
+#pragma unroll 1
       for (int s = 1; s <= 4; ++s) {
         // ---- potential at the stage point: gradient component gc of this mode, Hessian into shared memory
         double vpart = 0.0, gc = 0.0;
@@ -244,7 +274,8 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
           const int aa = a < D ? a : 0;
           const double up = __shfl_sync(FULL, u[aa], (lane + D) & 31);    // Mqp[a][c]
           const double vp = __shfl_sync(FULL, v[aa], (lane + D) & 31);    // Mpp[a][c]
-          const double sa = __ldg(E.sgt + aa), isa = __ldg(E.isgt + aa);
+          const double sa = cst[Cfg::O_SGT + aa], isa = cst[Cfg::O_ISGT + aa];
+          const double sgi_c = SC_PC(7), isgi_c = SC_PC(8);
           Cc[a] = make_double2(0.5 * (sa * u[aa] * isgi_c + isa * vp * sgi_c), 0.5 * (-sa * up * sgi_c + isa * v[aa] * isgi_c));
         }
       } else {
@@ -256,8 +287,8 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
             double t1 = 0.0, t2 = 0.0;
 #pragma unroll
             for (int a = 0; a < D; ++a) {
-              t1 = fma(__ldg(E.L1 + ap * D + a), u[a], t1);
-              t2 = fma(__ldg(E.L2 + ap * D + a), v[a], t2);
+              t1 = fma(cst[Cfg::O_L1 + ap * D + a], u[a], t1);
+              t2 = fma(cst[Cfg::O_L2 + ap * D + a], v[a], t2);
             }
             Tst[c * 2 * DR + ap] = t1;
             Tst[c * 2 * DR + DR + ap] = t2;
@@ -269,7 +300,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
         for (int ap = 0; ap < DR; ++ap) Cc[ap] = make_double2(0.0, 0.0);
 #pragma unroll
         for (int b = 0; b < D; ++b) {
-          const double r1 = __ldg(E.R1 + b * DR + cr), r2 = __ldg(E.R2 + b * DR + cr);
+          const double r1 = cst[Cfg::O_R1 + b * DR + cr], r2 = cst[Cfg::O_R2 + b * DR + cr];
           const double *Tq = Tst + b * 2 * DR, *Tp = Tst + (D + b) * 2 * DR;
 #pragma unroll
           for (int ap = 0; ap < DR; ++ap) {
@@ -318,11 +349,12 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
       }
       // ================= correlation contributions =================
       {
-        const double dq = q0c - qa, dp = p0c - pa;
+        const double p0c = SC_PC(1);
+        const double dq = SC_PC(0) - qa, dp = p0c - pa;
         double v0, v1;
         if (E.diag) {
-          v0 = -0.5 * (dq * oA * dq + dp * oB * dp);
-          v1 = -p0c * dq + dq * oC * dp;
+          v0 = -0.5 * (dq * SC_PC(4) * dq + dp * SC_PC(5) * dp);
+          v1 = -p0c * dq + dq * SC_PC(6) * dp;
         } else {
           if (mode_c) { dqv[c] = dq; dpv[c] = dp; }
           __syncwarp();
@@ -330,16 +362,16 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
           const int cm_ = c < D ? c : 0;
 #pragma unroll
           for (int j = 0; j < D; ++j) {
-            sa = fma(__ldg(E.otA + j * D + cm_), dqv[j], sa);
-            sb = fma(__ldg(E.otB + j * D + cm_), dpv[j], sb);
-            sc_ = fma(__ldg(E.otC + j * D + cm_), dqv[j], sc_);
+            sa = fma(cst[Cfg::O_OA + j * D + cm_], dqv[j], sa);
+            sb = fma(cst[Cfg::O_OB + j * D + cm_], dpv[j], sb);
+            sc_ = fma(cst[Cfg::O_OC + j * D + cm_], dqv[j], sc_);
           }
           v0 = -0.5 * (dq * sa + dp * sb);
           v1 = -p0c * dq + dp * sc_;
         }
         if (mode_c) {
-          red[0 * D + c] = v0; red[1 * D + c] = v1; red[2 * D + c] = dq * wrc; red[3 * D + c] = -dp * wgc;
-          red[4 * D + c] = v4c; red[5 * D + c] = v5c; red[6 * D + c] = accS; red[7 * D + c] = e4;
+          red[0 * D + c] = v0; red[1 * D + c] = v1; red[2 * D + c] = dq * SC_PC(2); red[3 * D + c] = -dp * SC_PC(3);
+          red[6 * D + c] = accS; red[7 * D + c] = e4;
         }
       }
       __syncwarp();
@@ -348,18 +380,19 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
         double v8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
+          const double *src = (i == 4) ? v4s : (i == 5) ? v5s : red + i * D;
           double sacc = 0.0;
 #pragma unroll
-          for (int a = 0; a < D; ++a) sacc += red[i * D + a];
+          for (int a = 0; a < D; ++a) sacc += src[a];
           v8[i] = sacc;
         }
-        S += h / 6.0 * v8[6];
-        sign = track_sign(sign, c2, det);
-        c2 = det;
-        cc = csqrt_principal(det);
+        const double S = lead[0] + h / 6.0 * v8[6];
+        const double sign = track_sign(lead[1], make_double2(lead[2], lead[3]), det);
+        const double2 cc = csqrt_principal(det);
+        lead[0] = S; lead[1] = sign; lead[2] = det.x; lead[3] = det.y; lead[4] = cc.x; lead[5] = cc.y;
         double2 ca, ki;
         const double v6[6] = {v8[0], v8[1], v8[2], v8[3], v8[4], v8[5]};
-        corr_finish(E, v6, S, cc, sign, wvi, ca, ki);
+        corr_finish(E, v6, S, cc, sign, make_double2(lead[6], lead[7]), ca, ki);
         row5[0] = ca.x; row5[1] = ca.y; row5[2] = ki.x; row5[3] = ki.y; row5[4] = v8[7];
       }
       if (NGW > 1) {
@@ -386,9 +419,9 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
         }
         if (c < D) { sr[c] = qa; sr[D + c] = pa; }
         if (c == 0) {
-          sr[2 * D] = S;
-          E.snap_c[item] = cc;
-          E.snap_sign[item] = sign;
+          sr[2 * D] = lead[0];
+          E.snap_c[item] = make_double2(lead[4], lead[5]);
+          E.snap_sign[item] = lead[1];
         }
       }
     }
@@ -401,14 +434,15 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
       }
       if (c < D) { rec[c] = qa; rec[D + c] = pa; }
       if (c == 0) {
-        rec[2 * D] = S;
-        E.c2[traj] = c2;
-        E.c[traj] = cc;
-        E.sign[traj] = sign;
+        rec[2 * D] = lead[0];
+        E.c2[traj] = make_double2(lead[2], lead[3]);
+        E.c[traj] = make_double2(lead[4], lead[5]);
+        E.sign[traj] = lead[1];
       }
     }
     __syncwarp();
   }
+#undef SC_PC
 }
 
 inline bool small_supported(const EngDev &E, const PotDev &P) {

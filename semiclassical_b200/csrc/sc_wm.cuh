@@ -640,6 +640,20 @@ __global__ void __launch_bounds__(128) k_wm(EngDev E, WMDev W, WMLayout L, int m
   }
 }
 
+// d beyond the shared-memory envelope (about 21 modes): the workspace of the CTA's trajectory lives in global memory (one slab
+// per CTA, mostly L1/L2 hits); same code, one group of TPT threads per CTA
+template <int TPT>
+__global__ void __launch_bounds__(TPT) k_wm_global(EngDev E, WMDev W, WMLayout L, int mode, double *partials, double2 *gws) {
+  const int t = threadIdx.x;
+  double2 *ws = gws + (size_t)blockIdx.x * L.total;
+  double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int traj = blockIdx.x; traj < E.n; traj += gridDim.x) wm_trajectory<TPT>(E, W, L, ws, traj, mode, t, 0, acc4);
+  if (t == 0 && mode != WM_INIT) {
+    double *row = partials + (size_t)blockIdx.x * 4;
+    row[0] = acc4[0]; row[1] = acc4[1]; row[2] = acc4[2]; row[3] = acc4[3];
+  }
+}
+
 // K time steps per launch: the HK kernel stored the record, sqrt(det) and sign of every (step, trajectory); a group walks the
 // steps of its trajectory IN TIME ORDER (the detA / detM branch trackers are sequential) and adds the contributions of step k
 // to its own row k of partials (ngroups, K, 4) -- zeroed by the host, one writer per row

@@ -168,6 +168,41 @@ def test_wm_fused_propagate_matches_reference(name, cuda_device):
     _check_wm_signs(pr, g)
 
 
+@pytest.mark.parametrize("d,rotated", [(24, False), (24, True), (60, False)])
+def test_wm_beyond_shared_memory_envelope(d, rotated, cuda_device):
+    """Walton-Manolopoulos above about 21 modes: the per-trajectory workspace (30 d^2 complex numbers) no longer fits in
+    shared memory and lives in global-memory slabs (k_wm_global).  AS model with d modes (optionally rotated: dense
+    Hessians and dense widths) against the C oracle, three branch trackers bit-identical."""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_synthetic(d, 0.02)
+    if rotated:
+        Q = workloads.random_orthogonal(d)
+        G = Q @ np.diag(m.omega) @ Q.T
+        G = 0.5 * (G + G.T)
+        q0, p0 = Q @ m.q0, Q @ m.p0
+        opot = oracle.Potential.rotated_morse(m.omega, m.chi, m.nac, Q)
+        pot = potentials.RotatedMorsePotential(T(m.omega), T(m.chi), T(m.nac), T(Q))
+    else:
+        G, q0, p0 = np.diag(m.omega), m.q0, m.p0
+        opot = oracle.Potential.morse(m.omega, m.chi, m.nac)
+        pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    n, nt = 40, 6
+    zi, probi = oracle.sample_ensemble(G, G, q0, p0, n, np.random.default_rng(5))
+    dt, _ = workloads.test_time_grid()
+    ref = oracle.run(opot, oracle.Consts(G, G, G, q0, p0, alpha=500.0, beta=500.0), zi, probi, dt, nt, m.en_zpt, wm=True)
+    pr = propagators.WaltonManolopoulosPropagator(T(G), T(G), 500, 500, device=cuda_device)
+    pr.set_ensemble(T(q0), T(p0), T(G), T(zi), T(probi))
+    auto, ic = run_loop(pr, pot, dt, nt, m.en_zpt)
+    assert pr.kernel_name().endswith("k_wm_global")
+    assert relerr(auto, ref['autocorrelation']) < TOL
+    assert relerr(ic, ref['ic_correlation']) < TOL
+    st = pr.sign_trackers
+    assert np.array_equal(st["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
+    assert np.array_equal(st["detA"]["signs"].real.cpu().numpy(), ref['signs'][1])
+    assert np.array_equal(st["detM"]["signs"].real.cpu().numpy(), ref['signs'][2])
+
+
 def test_c2_full_size_wm_fused_launches(cuda_device):
     """BASELINE configs[1] at its FULL size: AS 5 modes, WM alpha = beta = 500, 10^4 trajectories, 100 steps, against the
     reference's golden (ensemble regenerated from its numpy seed).  K-step fused launches (k_hk_generic snapshots +
