@@ -364,7 +364,10 @@ static int wm_alloc(WMState &w, DevPool &ens, const EngDev &D, const double *q0_
   int per_sm = (int)((227 * 1024) / (w.smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2048 / (w.tpt * w.groups)) per_sm = 2048 / (w.tpt * w.groups);
-  if (w.global_ws) per_sm = 3;
+  if (w.global_ws) {
+    per_sm = 3;
+    if (const char *s = getenv("SC_WM_CTAS")) per_sm = std::max(1, std::min(8, atoi(s)));
+  }
   int grid = sm_count * per_sm;
   const int need = (n + w.groups - 1) / w.groups;
   if (grid > need) grid = need;

@@ -43,7 +43,8 @@ __device__ __forceinline__ double2 pick_row(const double2 (&col)[N], int p) {
   return r;
 }
 
-template <int D, int DR>
+// PT / DG: potential type and diagonal-width flag folded at compile time (-1: read from the arguments)
+template <int D, int DR, int PT = -1, int DG = -1>
 __global__ void __launch_bounds__(128, SmallCfg<D, DR>::MIN_CTAS)
 k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
   using Cfg = SmallCfg<D, DR>;
@@ -59,7 +60,9 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
   double *Hs = gs, *hdv = Hs + D * LDH, *qs = hdv + LDH, *scr = qs + LDH, *scr2 = scr + LDH, *dqv = scr2 + LDH,
          *dpv = dqv + LDH, *v4s = dpv + LDH, *v5s = v4s + LDH, *Tst = v5s + LDH, *red = Tst + GS * 2 * DR, *lead = red + 8 * D;
   // lead: state of the group's leader thread (S, sign, det, sqrt(det), initial overlap), kept out of everybody's registers
-  const int ptype = P.type;
+  const int ptype = PT >= 0 ? PT : P.type;
+  const bool diag = DG >= 0 ? (DG != 0) : (E.diag != 0);
+  const bool all_harmonic = (PT == POT_MORSE && DG == 1) ? false : (P.all_harmonic != 0);   // the compile-time Morse case is anharmonic
   const bool separable = ptype == POT_MORSE || ptype == POT_NONHARMONIC;
   for (int i = threadIdx.x; i < D * D; i += blockDim.x) {
     const int a = i / D, k = i % D;
@@ -73,11 +76,11 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
     for (int i = t; i < D; i += nt) {
       double *pc = cst + Cfg::O_PC + i;
       pc[0] = E.q0[i]; pc[LDH] = E.p0[i]; pc[2 * LDH] = E.wR[i]; pc[3 * LDH] = E.wG[i];
-      if (E.diag) {
+      if (diag) {
         pc[4 * LDH] = E.otA[i]; pc[5 * LDH] = E.otB[i]; pc[6 * LDH] = E.otC[i]; pc[7 * LDH] = E.sgi[i]; pc[8 * LDH] = E.isgi[i];
       }
     }
-    if (E.diag) {
+    if (diag) {
       for (int i = t; i < D; i += nt) { cst[Cfg::O_SGT + i] = E.sgt[i]; cst[Cfg::O_ISGT + i] = E.isgt[i]; }
     } else {
       for (int i = t; i < DR * D; i += nt) {
@@ -100,7 +103,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
     im_c = P.imass[c];
     if (ptype == POT_HARMONIC) { pos0c = P.pos0[c]; grad0c = P.grad0[c]; }
     if (ptype == POT_MORSE || ptype == POT_ROTATED_MORSE) {
-      if (P.all_harmonic) pa1 = P.omega[c] * P.omega[c];
+      if (all_harmonic) pa1 = P.omega[c] * P.omega[c];
       else { pa1 = P.a[c]; pa2 = P.D[c]; }
     }
     if (ptype == POT_NONHARMONIC) { pa1 = P.eps[c]; pa2 = P.b[c]; }
@@ -137,7 +140,8 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
 #pragma unroll
       for (int a = 0; a < D; ++a) { us[a] = u[a]; R1[a] = 0.0; R2[a] = 0.0; }
       double qsa = qa, psa = pa, accq = 0, accp = 0, accS = 0, e4 = 0;
-#pragma unroll 1
+      constexpr int STAGE_UNROLL = (PT >= 0) ? 4 : 1;     // the folded kernels are small enough to unroll the stages
+#pragma unroll STAGE_UNROLL
       for (int s = 1; s <= 4; ++s) {
         // ---- potential at the stage point: gradient component gc of this mode, Hessian into shared memory
         double vpart = 0.0, gc = 0.0;
@@ -146,7 +150,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
           if (mode_c) {
             double hd;
             if (ptype == POT_MORSE) {
-              if (P.all_harmonic) {
+              if (all_harmonic) {
                 vpart = 0.5 * pa1 * qsa * qsa; gc = pa1 * qsa; hd = pa1;
               } else {
                 const double e = exp(-pa1 * qsa);
@@ -182,7 +186,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
 #pragma unroll
             for (int i = 0; i < D; ++i) r = fma(cmat[i * LDH + c], qs[i], r);
             double gi, hi;
-            if (P.all_harmonic) {
+            if (all_harmonic) {
               vpart = 0.5 * pa1 * r * r; gi = pa1 * r; hi = pa1;
             } else {
               const double e = exp(-pa1 * r);
@@ -267,7 +271,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
       }
       // ================= prefactor matrix, column c on thread c < DR =================
       double2 Cc[DR];
-      if (E.diag) {
+      if (diag) {
         // diagonal width matrices (d' = d): element-wise scaling; the p-half columns live D lanes further up
 #pragma unroll
         for (int a = 0; a < DR; ++a) {
@@ -352,7 +356,7 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
         const double p0c = SC_PC(1);
         const double dq = SC_PC(0) - qa, dp = p0c - pa;
         double v0, v1;
-        if (E.diag) {
+        if (diag) {
           v0 = -0.5 * (dq * SC_PC(4) * dq + dp * SC_PC(5) * dp);
           v1 = -p0c * dq + dq * SC_PC(6) * dp;
         } else {
@@ -453,11 +457,11 @@ inline bool small_supported(const EngDev &E, const PotDev &P) {
          (d == 12 && dr == 12);
 }
 
-template <int D, int DR>
+template <int D, int DR, int PT = -1, int DG = -1>
 static cudaError_t launch_small_t(int sm_count, const EngDev &E, const PotDev &P, double h, int nsteps, double *partials,
                                   int &nrows_groups, bool plan_only, cudaStream_t st) {
   using Cfg = SmallCfg<D, DR>;
-  auto kern = k_hk_small<D, DR>;
+  auto kern = k_hk_small<D, DR, PT, DG>;
   static int per_sm = 0;
   if (per_sm == 0) {
     cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
@@ -481,6 +485,11 @@ inline cudaError_t launch_small(int sm_count, const EngDev &E, const PotDev &P, 
                                 int &nrows_groups, bool plan_only, cudaStream_t st) {
 #define SC_SMALL_CASE(D_, R_) \
   if (E.d == D_ && E.dr == R_) return launch_small_t<D_, R_>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st)
+  // the two small BASELINE configs with everything folded: C1 / C2 (anharmonic Morse, diagonal widths), C3 (harmonic, dense widths)
+  if (E.d == 5 && E.dr == 5 && P.type == POT_MORSE && E.diag && !P.all_harmonic)
+    return launch_small_t<5, 5, POT_MORSE, 1>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st);
+  if (E.d == 12 && E.dr == 6 && P.type == POT_HARMONIC && !E.diag)
+    return launch_small_t<12, 6, POT_HARMONIC, 0>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st);
   SC_SMALL_CASE(1, 1);
   SC_SMALL_CASE(2, 2);
   SC_SMALL_CASE(3, 3);
