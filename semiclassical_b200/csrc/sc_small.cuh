@@ -1,4 +1,5 @@
-// sc_small.cuh -- fused Herman-Kluk step kernel for small systems (d <= 12): register-resident monodromy columns.
+// sc_small.cuh -- fused Herman-Kluk step kernel for small systems (d = 1..6, 8, 9, 12; any rank d' <= d): register-resident
+// monodromy columns.
 //
 // k_hk_generic (sc_kernels.cuh) gives a whole warp to one trajectory and keeps its state in shared memory; at d = 5 that
 // is 100 monodromy elements on 32 lanes, three shared-memory round trips per element and stage, and a warp-wide barrier
@@ -83,8 +84,16 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
     if (diag) {
       for (int i = t; i < D; i += nt) { cst[Cfg::O_SGT + i] = E.sgt[i]; cst[Cfg::O_ISGT + i] = E.isgt[i]; }
     } else {
+      // rank d' <= DR: the factors are zero-padded to DR rows / columns and the padded diagonal of the prefactor matrix is
+      // set to one below, which leaves the determinant unchanged
+      const int dr = E.dr;
       for (int i = t; i < DR * D; i += nt) {
-        cst[Cfg::O_L1 + i] = E.L1[i]; cst[Cfg::O_L2 + i] = E.L2[i]; cst[Cfg::O_R1 + i] = E.R1[i]; cst[Cfg::O_R2 + i] = E.R2[i];
+        const int ap = i / D;                                  // L1, L2: (d' x d) row-major
+        cst[Cfg::O_L1 + i] = ap < dr ? E.L1[i] : 0.0;
+        cst[Cfg::O_L2 + i] = ap < dr ? E.L2[i] : 0.0;
+        const int b = i / DR, j = i % DR;                      // R1, R2: (d x d') row-major
+        cst[Cfg::O_R1 + i] = j < dr ? E.R1[b * dr + j] : 0.0;
+        cst[Cfg::O_R2 + i] = j < dr ? E.R2[b * dr + j] : 0.0;
       }
       for (int i = t; i < D * D; i += nt) { cst[Cfg::O_OA + i] = E.otA[i]; cst[Cfg::O_OB + i] = E.otB[i]; cst[Cfg::O_OC + i] = E.otC[i]; }
     }
@@ -313,7 +322,11 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
           }
         }
 #pragma unroll
-        for (int ap = 0; ap < DR; ++ap) { Cc[ap].x *= 0.5; Cc[ap].y *= 0.5; }
+        for (int ap = 0; ap < DR; ++ap) {
+          Cc[ap].x *= 0.5;
+          Cc[ap].y *= 0.5;
+          if (ap >= E.dr && ap == c) Cc[ap].x = 1.0;             // identity on the padded diagonal (d' < DR)
+        }
       }
       // ================= determinant: column-distributed LU, implicit partial pivoting =================
       double2 det = make_double2(1.0, 0.0);
@@ -452,9 +465,8 @@ k_hk_small(EngDev E, PotDev P, double h, int nsteps, double *partials) {
 inline bool small_supported(const EngDev &E, const PotDev &P) {
   if (!(P.type == POT_MORSE || P.type == POT_NONHARMONIC || P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE)) return false;
   if (E.diag && E.dr != E.d) return false;
-  const int d = E.d, dr = E.dr;
-  return (d == 1 && dr == 1) || (d == 2 && dr == 2) || (d == 3 && dr == 3) || (d == 5 && dr == 5) || (d == 12 && dr == 6) ||
-         (d == 12 && dr == 12);
+  const int d = E.d;
+  return (d >= 1 && d <= 6) || d == 8 || d == 9 || d == 12;     // any rank d' <= d (zero-padded factors)
 }
 
 template <int D, int DR, int PT = -1, int DG = -1>
@@ -490,12 +502,12 @@ inline cudaError_t launch_small(int sm_count, const EngDev &E, const PotDev &P, 
     return launch_small_t<5, 5, POT_MORSE, 1>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st);
   if (E.d == 12 && E.dr == 6 && P.type == POT_HARMONIC && !E.diag)
     return launch_small_t<12, 6, POT_HARMONIC, 0>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st);
-  SC_SMALL_CASE(1, 1);
-  SC_SMALL_CASE(2, 2);
-  SC_SMALL_CASE(3, 3);
-  SC_SMALL_CASE(5, 5);
   SC_SMALL_CASE(12, 6);
-  SC_SMALL_CASE(12, 12);
+#undef SC_SMALL_CASE
+#define SC_SMALL_CASE(D_) \
+  if (E.d == D_) return launch_small_t<D_, D_>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st)
+  SC_SMALL_CASE(1); SC_SMALL_CASE(2); SC_SMALL_CASE(3); SC_SMALL_CASE(4); SC_SMALL_CASE(5); SC_SMALL_CASE(6);
+  SC_SMALL_CASE(8); SC_SMALL_CASE(9); SC_SMALL_CASE(12);
 #undef SC_SMALL_CASE
   return cudaErrorInvalidValue;
 }

@@ -650,6 +650,35 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
+@pytest.mark.parametrize("d,nzero", [(2, 0), (3, 1), (4, 2), (6, 0), (6, 3), (8, 2), (9, 3), (12, 5), (12, 0)])
+def test_small_systems_any_rank(d, nzero, cuda_device):
+    """k_hk_small with dense width matrices of rank d' = d - nzero <= d (the factors are zero-padded to d and the padded
+    diagonal of the prefactor matrix set to one): dense harmonic 'molecules' with 2 ... 12 coordinates against the C oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.harmonic_molecule_synthetic(d, nzero, seed=40 + d)
+    G = m['Gamma_0']
+    n, nt = 131, 12
+    zi, probi = oracle.sample_ensemble(G, G, m['q0'], m['p0'], n, np.random.default_rng(300 + d))
+    dt, _ = workloads.test_time_grid()
+    opot = oracle.Potential.harmonic(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    ref = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt, m['en_zpt'])
+    pot = potentials.MolecularHarmonicPotential.from_arrays(m['pos0'], m['energy0'], m['grad0'], m['hess0'], m['masses'], m['nac'])
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m['q0']), T(m['p0']), T(G), T(zi), T(probi))
+    assert pr.rank == d - nzero
+    a0, i0 = pr.autocorrelation(m['en_zpt']), pr.ic_correlation(pot, m['en_zpt'])
+    a, i = pr.propagate(pot, dt, nt - 1, m['en_zpt'])
+    assert pr.kernel_name() == "k_hk_small"
+    assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    ref2 = oracle.run(opot, oracle.Consts(G, G, G, m['q0'], m['p0']), zi, probi, dt, nt, m['en_zpt'])
+    assert relerr(pr.y.cpu().numpy(), ref2['y']) < TOL
+    assert relerr(pr.c.cpu().numpy(), ref2['c']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
+
+
 @pytest.mark.parametrize("d,n,nt", [(17, 1, 4), (18, 2, 5), (31, 149, 4), (32, 3, 37), (33, 150, 3), (47, 297, 3), (61, 5, 4), (65, 7, 3),
                                     (80, 151, 3)])
 def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
