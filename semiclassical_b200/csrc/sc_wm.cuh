@@ -238,7 +238,11 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     A[idx] = make_double2(2.0 * f + mg + gi, -hs + 2.0 * (pm - ee));
   }
   gsync<TPT>(gid);
+  // full-rank widths: U is orthogonal, the projection A' = U2^T A U2 is a similarity transform (same determinant, and
+  // U2 A'^-1 U2^T = A^-1), so the four projection products are skipped and A is inverted in place of A'
+  const bool fullrank = (dr == d);
   // A' = U2^T A U2 with U2 = blockdiag(U, U)
+  if (!fullrank)
   for (int idx = t; idx < R2 * D2; idx += TPT) {
     const int a = idx / D2, j = idx % D2;
     const int off = (a < dr) ? 0 : d, aa = (a < dr) ? a : a - dr;
@@ -251,7 +255,8 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     T1[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
+  if (!fullrank)
   for (int idx = t; idx < R2 * R2; idx += TPT) {
     const int a = idx / R2, b = idx % R2;
     const int off = (b < dr) ? 0 : d, bb = (b < dr) ? b : b - dr;
@@ -264,10 +269,12 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     AP[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
   // A'^-1 and det(A' / (2 sqrt(alpha beta)))   (propagators.py:1255, 1328-1332)
-  const double2 detA = gj_inverse<TPT>(AP, IAP, R2, 1.0 / (2.0 * sqrt(W.alpha * W.beta)), col, t, gid);
+  const double2 detA = gj_inverse<TPT>(fullrank ? A : AP, IAP, R2, 1.0 / (2.0 * sqrt(W.alpha * W.beta)), col, t, gid);
+  const double2 *Ainv = fullrank ? IAP : A;
   // A^-1 = U2 A'^-1 U2^T  -> A
+  if (!fullrank)
   for (int idx = t; idx < D2 * R2; idx += TPT) {
     const int i = idx / R2, b = idx % R2;
     const int off = (i < d) ? 0 : dr, ii = (i < d) ? i : i - d;
@@ -280,7 +287,8 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     T1[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
+  if (!fullrank)
   for (int idx = t; idx < D2 * D2; idx += TPT) {
     const int i = idx / D2, j = idx % D2;
     const int off = (j < d) ? 0 : dr, jj = (j < d) ? j : j - d;
@@ -293,13 +301,13 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     A[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
   // T1 = BQ A^-1  (d x 2d)
   for (int idx = t; idx < d * D2; idx += TPT) {
     const int i = idx / D2, k = idx % D2;
     double2 s = make_double2(0.0, 0.0);
     for (int j = 0; j < D2; ++j) {
-      const double2 b = BQ[i * D2 + j], v = A[j * D2 + k];
+      const double2 b = BQ[i * D2 + j], v = Ainv[j * D2 + k];
       s.x += b.x * v.x - b.y * v.y;
       s.y += b.x * v.y + b.y * v.x;
     }
@@ -440,7 +448,10 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     gsync<TPT>(gid);
     return;
   }
-  // eqn (78): M = Gamma_0 + CQQ, projected: M' = U^T M U
+  // eqn (78): M = Gamma_0 + CQQ, projected: M' = U^T M U   (full rank: M itself, see above)
+  if (fullrank)
+    for (int idx = t; idx < d2; idx += TPT) MPr[idx] = make_double2(SC_LDG(W.G0 + idx) + CQQ[idx].x, CQQ[idx].y);
+  if (!fullrank)
   for (int idx = t; idx < dr * d; idx += TPT) {
     const int a = idx / d, j = idx % d;
     double2 s = make_double2(0.0, 0.0);
@@ -451,7 +462,8 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     T1[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
+  if (!fullrank)
   for (int idx = t; idx < dr * dr; idx += TPT) {
     const int a = idx / dr, b = idx % dr;
     double2 s = make_double2(0.0, 0.0);
@@ -464,7 +476,9 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
   }
   gsync<TPT>(gid);
   const double2 detM = gj_inverse<TPT>(MPr, IMP, dr, 1.0 / (2.0 * M_PI), col, t, gid);
+  const double2 *IMi = fullrank ? IMP : IM;
   // M^-1 = U M'^-1 U^T
+  if (!fullrank)
   for (int idx = t; idx < d * dr; idx += TPT) {
     const int i = idx / dr, b = idx % dr;
     double2 s = make_double2(0.0, 0.0);
@@ -475,7 +489,8 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     T1[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
+  if (!fullrank)
   for (int idx = t; idx < d2; idx += TPT) {
     const int i = idx / d, j = idx % d;
     double2 s = make_double2(0.0, 0.0);
@@ -486,13 +501,13 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
     }
     IM[idx] = s;
   }
-  gsync<TPT>(gid);
+  if (!fullrank) gsync<TPT>(gid);
   // X1 = CqQ M^-1 ; X2 = Gamma_0 M^-1
   for (int idx = t; idx < d2; idx += TPT) {
     const int i = idx / d, k = idx % d;
     double2 s = make_double2(0.0, 0.0), g = make_double2(0.0, 0.0);
     for (int j = 0; j < d; ++j) {
-      const double2 c = CqQ[i * d + j], m = IM[j * d + k];
+      const double2 c = CqQ[i * d + j], m = IMi[j * d + k];
       s.x += c.x * m.x - c.y * m.y;
       s.y += c.x * m.y + c.y * m.x;
       const double g0 = SC_LDG(W.G0 + i * d + j);
@@ -530,8 +545,8 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
       s1.y += X1[i * d + k].x * v.y + X1[i * d + k].y * v.x;
       s2.x += X2[i * d + k].x * v.x - X2[i * d + k].y * v.y;
       s2.y += X2[i * d + k].x * v.y + X2[i * d + k].y * v.x;
-      s3.x += IM[i * d + k].x * v.x - IM[i * d + k].y * v.y;
-      s3.y += IM[i * d + k].x * v.y + IM[i * d + k].y * v.x;
+      s3.x += IMi[i * d + k].x * v.x - IMi[i * d + k].y * v.y;
+      s3.y += IMi[i * d + k].x * v.y + IMi[i * d + k].y * v.x;
     }
     Pq[i] = make_double2(PIq[i] - s1.x, -s1.y);
     PQ[i] = make_double2(SC_LDG(W.p0 + i) + s2.x, s2.y);
