@@ -679,6 +679,33 @@ def test_small_systems_any_rank(d, nzero, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
+@pytest.mark.parametrize("d,n,nt", [(1, 1, 5), (1, 17, 40), (5, 1, 6), (5, 2, 6), (5, 7, 130), (5, 1777, 4), (12, 1, 5), (12, 5, 70),
+                                    (3, 11, 9), (9, 3, 9)])
+def test_small_kernel_edge_shapes(d, n, nt, cuda_device):
+    """k_hk_small on ragged ensembles: a single trajectory (one group of a warp active), fewer trajectories than groups per
+    warp, ensembles that are not a multiple of the trajectories per warp / CTA, more steps per launch than any other test
+    (129 fused steps), AS model with d modes against the C oracle"""
+    from oracle import oracle
+    from semiclassical_b200 import workloads, potentials, propagators
+    m = workloads.as_synthetic(d, 0.02) if d != 5 else workloads.as_5modes(0.02)
+    G = np.diag(m.omega)
+    zi, probi = oracle.sample_ensemble(G, G, m.q0, m.p0, n, np.random.default_rng(900 + 10 * d + n))
+    dt, _ = workloads.test_time_grid()
+    ref = oracle.run(oracle.Potential.morse(m.omega, m.chi, m.nac), oracle.Consts(G, G, G, m.q0, m.p0), zi, probi, dt, nt, m.en_zpt)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    pr = propagators.HermanKlukPropagator(T(G), T(G), device=cuda_device)
+    pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
+    a0, i0 = pr.autocorrelation(m.en_zpt), pr.ic_correlation(pot, m.en_zpt)
+    a, i = pr.propagate(pot, dt, nt - 1, m.en_zpt)
+    assert pr.kernel_name() == "k_hk_small"
+    assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
+    assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
+    pr.step(pot, dt)
+    assert relerr(pr.y.cpu().numpy(), ref['y']) < TOL
+    assert relerr(pr.c.cpu().numpy(), ref['c']) < TOL
+    assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
+
+
 @pytest.mark.parametrize("d,n,nt", [(17, 1, 4), (18, 2, 5), (31, 149, 4), (32, 3, 37), (33, 150, 3), (47, 297, 3), (61, 5, 4), (65, 7, 3),
                                     (80, 151, 3)])
 def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
