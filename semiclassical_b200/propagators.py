@@ -532,6 +532,17 @@ class HermanKlukPropagator(object):
         c, _, signs = self._prefactor_arrays()
         return signs[0] * c
 
+    def autocorrelation_qp(self):
+        """contribution of each trajectory to the autocorrelation function, <phi(0)|qt,pt> C(t) e^{iS} <qi,pi|phi(0)>
+        (propagators.py:784-807).  Diagnostic accessor: torch operations on the exported state; the correlation functions
+        themselves are accumulated inside the step kernels."""
+        qi, pi = self.initial_positions_and_momenta()
+        qt, pt = self.current_positions_and_momenta()
+        q0, p0 = self.q0.to(self.device), self.p0.to(self.device)
+        vi = self.csoi0(qi, pi, q0, p0).squeeze()
+        vt = self.csot0(qt, pt, q0, p0).squeeze()
+        return vt.conj() * vi * self.semiclassical_prefactor() * torch.exp(1j / hbar * self.classical_action())
+
     # ------------------------------------------------------------------ wavefunction diagnostics (propagators.py:657-782)
     def coefficients(self):
         """
@@ -643,6 +654,11 @@ class WaltonManolopoulosPropagator(HermanKlukPropagator):
         self.alpha = torch.tensor(alpha)
         self.beta = torch.tensor(beta)
         self._wm = 1
+
+    def autocorrelation_qp(self):
+        # the per-trajectory WM contributions (eqn 85, propagators.py:1577-1632) exist only inside k_wm / k_wm_fused
+        raise NotImplementedError("per-trajectory contributions are not exported for the Walton-Manolopoulos propagator; "
+                                  "autocorrelation() and ic_correlation() return the sums")
 
     @property
     def sign_trackers(self):

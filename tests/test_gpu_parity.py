@@ -56,6 +56,23 @@ def test_hk_fused_propagate_matches_reference(name, cuda_device):
     assert relerr(np.concatenate(([i0], i)), g['ic_correlation']) < TOL
 
 
+@pytest.mark.parametrize("name", ["hk_as5_chi002", "hk_methylium"])
+def test_per_trajectory_contributions_sum_to_autocorrelation(name, cuda_device):
+    """autocorrelation_qp() (propagators.py:784-807): the Monte-Carlo sum of the per-trajectory contributions is the
+    autocorrelation function the step kernels accumulate"""
+    g = helpers.load_golden(name)
+    pot = helpers.potential_from_golden(g)
+    pr = helpers.propagator_from_golden(g, cuda_device)
+    e0, dt = float(g['energy0_es']), float(g['dt'])
+    for k in range(3):
+        qp = pr.autocorrelation_qp()
+        assert qp.shape == (pr.ntraj,)
+        total = torch.sum(qp / (pr.ntraj * pr.probi * (2 * np.pi)**pr.dim)) * np.exp(1j * float(pr.t) * e0)
+        assert abs(complex(total) - g['autocorrelation'][k]) < 1e-11 * max(1.0, abs(g['autocorrelation'][k]))
+        assert abs(complex(total) - pr.autocorrelation(e0)) < 1e-11
+        pr.step(pot, dt)
+
+
 def test_initial_autocorrelation_is_one(cuda_device):
     g = helpers.load_golden("hk_as5_chi002")
     pr = helpers.propagator_from_golden(g, cuda_device)
