@@ -334,7 +334,7 @@ static int wm_setup(WMState &w, const sc_engine_config &cfg, DevPool &pool) {
   w.smem = ws * w.groups;
   w.global_ws = false;
   if (w.smem > 227 * 1024) {
-    // beyond about 21 modes the workspace of one trajectory does not fit in shared memory: slabs in global memory
+    // beyond about 29 modes (21 for rank-deficient widths) the workspace of one trajectory does not fit in shared memory: slabs in global memory
     w.global_ws = true;
     w.tpt = 256;
     w.groups = 1;

@@ -58,6 +58,27 @@ __host__ __device__ inline WMLayout make_wm_layout(int d, int dr) {
   WMLayout L;
   const int D2 = 2 * d, R2 = 2 * dr, d2 = d * d;
   int o = 0;
+  if (dr == d) {
+    // full-rank widths: no projections (wm_trajectory), A is inverted in place of A', and the arrays that are born after
+    // Gt~ / Gti (eqns 57, 59) reuse the space of those that are dead by then -- A (destroyed by the inversion), A^-1 and BQ
+    // (last read by eqns 57, 59).  494 instead of 894 complex numbers at d = 5: four CTAs of four trajectories per SM
+    // instead of three, and 0.77 MB instead of 1.8 MB per slab at d = 60
+    L.mq = o; o += d * D2;
+    L.vr = o; o += 4 * d;
+    L.bq = o; o += d * D2;
+    L.a = o; o += D2 * D2;
+    L.t1 = o; o += d * D2;
+    L.ap = L.a;
+    L.iap = o; o += R2 * R2;
+    L.gt = o; o += d2;
+    L.gti = o; o += d2;
+    L.x1 = L.a; L.cqQ = L.a + d2; L.cQQ = L.a + 2 * d2; L.x2 = L.a + 3 * d2;
+    L.rqq = L.iap; L.rQQ = L.iap + d2; L.rqQ = L.iap + 2 * d2; L.mp = L.iap + 3 * d2;
+    L.imp = L.bq; L.im = L.bq + d2;
+    L.vc = o; o += 12 * d + R2 + 4;
+    L.total = o;
+    return L;
+  }
   L.mq = o; o += d * D2;            // [Mqq|Mqp], [Mpq|Mpp] as two real d x 2d arrays
   L.vr = o; o += 4 * d;             // real vectors: Q, P, qi, pi, dq, dQ, v2, PIq
   L.bq = o; o += d * D2;
@@ -655,7 +676,7 @@ __global__ void __launch_bounds__(128) k_wm(EngDev E, WMDev W, WMLayout L, int m
   }
 }
 
-// d beyond the shared-memory envelope (about 21 modes): the workspace of the CTA's trajectory lives in global memory (one slab
+// d beyond the shared-memory envelope (about 29 modes; 21 for rank-deficient widths): the workspace of the CTA's trajectory lives in global memory (one slab
 // per CTA, mostly L1/L2 hits); same code, one group of TPT threads per CTA
 template <int TPT>
 __global__ void __launch_bounds__(TPT) k_wm_global(EngDev E, WMDev W, WMLayout L, int mode, double *partials, double2 *gws) {
@@ -673,7 +694,7 @@ __global__ void __launch_bounds__(TPT) k_wm_global(EngDev E, WMDev W, WMLayout L
 // steps of its trajectory IN TIME ORDER (the detA / detM branch trackers are sequential) and adds the contributions of step k
 // to its own row k of partials (ngroups, K, 4) -- zeroed by the host, one writer per row
 template <int TPT, int DC = 0>
-__global__ void __launch_bounds__(128) k_wm_fused(EngDev E, WMDev W, WMLayout L, int nsteps, double *partials) {
+__global__ void __launch_bounds__(128, (DC == 5 ? 4 : 1)) k_wm_fused(EngDev E, WMDev W, WMLayout L, int nsteps, double *partials) {
   extern __shared__ __align__(16) double2 wm_smem[];
   const int G = blockDim.x / TPT, gid = threadIdx.x / TPT, t = threadIdx.x % TPT;
   const int gg = blockIdx.x * G + gid, NG = gridDim.x * G;
