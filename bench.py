@@ -19,6 +19,8 @@ The JSON line carries
                     as_d60_dense_engine : the same AS ensemble, Hessians expanded to full per-trajectory matrices
                     harmonic_d60        : dense harmonic molecule-like model, d = 60, d' = 54, dense width matrices
                     rotated_as_d60      : rotated AS model, per-trajectory dense Hessians + dense width matrices
+  other_configs   (N = 1, informational) trajectory-steps/s of the remaining BASELINE.json configs through the same public API,
+                  state resident: C1 (AS 5 modes, HK), C2 (AS 5 modes, WM), C3 (methylium, harmonic), C5 (synthetic sGDML N = 17)
   peak            FP64 tensor-pipe peak measured in this run (sc_measure_fp64_peak: DMMA.8x8x4 chains on every SM)
 `--impl reference` times the CPU oracle port (oracle/sc_oracle.c, OpenMP over all host cores) on a bounded sample of
 the same workload -- the reference itself is pure Python and does not exist on the GPU box.
@@ -121,6 +123,63 @@ def cpu_run(model, G, Q, q0, p0, ntraj, nsteps, seed=0):
     oracle.run(pot, consts, zi, probi, dt, nsteps, model.en_zpt, nthreads=ncpu, want_state=False)
     el = time.perf_counter() - t0
     return ntraj * nsteps / el, oracle.lib().sc_oracle_num_threads(), el
+
+
+def other_configs(device):
+    """throughput of the remaining BASELINE.json configs (C1, C2, C3, C5: parity-test cases, not the headline) through the
+    public API with the state resident, ensembles sampled on the device; informational block of the N = 1 line"""
+    import torch
+    from semiclassical_b200 import workloads, potentials, propagators
+    T = lambda x: torch.from_numpy(np.ascontiguousarray(x))  # noqa: E731
+    out = {}
+
+    def run(tag, pr, pot, q0, p0, G0, n, dt, K, e0, reps=2):
+        try:
+            torch.manual_seed(0)
+            pr.initial_conditions(T(q0), T(p0), T(G0), ntraj=n)
+            pr.propagate(pot, dt, K, e0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                pr.propagate(pot, dt, K, e0)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / reps
+            out[tag] = {"ntraj": n, "dim": pr.dim, "steps_per_launch": K, "trajectory_steps_per_s": n * K / ms * 1e3,
+                        "kernel": pr.kernel_name()}
+        except Exception as e:                                   # never let an informational leg break the bench line
+            out[tag] = {"error": repr(e)[:200]}
+        finally:
+            del pr
+            gc.collect()
+            torch.cuda.empty_cache()
+
+    dt5, _ = workloads.test_time_grid()
+    m = workloads.as_5modes(0.02)
+    G = np.diag(m.omega)
+    pot = potentials.MorsePotential(T(m.omega), T(m.chi), T(m.nac))
+    run("C1 AS 5 modes HK", propagators.HermanKlukPropagator(T(G), T(G), device=device), pot, m.q0, m.p0, G, 1000000, dt5, 50, m.en_zpt)
+    run("C2 AS 5 modes WM alpha=beta=500", propagators.WaltonManolopoulosPropagator(T(G), T(G), 500, 500, device=device), pot,
+        m.q0, m.p0, G, 200000, dt5, 20, m.en_zpt)
+    try:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "hk_methylium.npz"), allow_pickle=False))
+        potm = potentials.MolecularHarmonicPotential.from_arrays(g['pos0'], g['energy0'], g['grad0'], g['hess0'], g['masses'], g['nac'],
+                                                                 float(g['origin']))
+        run("C3 methylium harmonic HK (d'=6)", propagators.HermanKlukPropagator(T(g['Gamma_i']), T(g['Gamma_t']), device=device), potm,
+            g['q0'], g['p0'], g['Gamma_0'], 100000, float(g['dt']), 100, float(g['energy0_es']))
+    except Exception as e:
+        out["C3 methylium harmonic HK (d'=6)"] = {"error": repr(e)[:200]}
+    try:
+        model, pos = workloads.gdml_synthetic()
+        dg = len(pos)
+        potg = potentials.MolecularGDMLPotential.from_arrays(model, np.full(dg, 12.0 * 1822.888486192), 1.0e-3 * np.ones(dg))
+        Gg = np.diag(np.full(dg, 20.0))
+        run("C5 synthetic sGDML N=17 HK", propagators.HermanKlukPropagator(T(Gg), T(Gg), device=device), potg, pos, np.zeros(dg), Gg,
+            20000, 0.5, 5, 0.0)
+    except Exception as e:
+        out["C5 synthetic sGDML N=17 HK"] = {"error": repr(e)[:200]}
+    return out
 
 
 def main():
@@ -407,6 +466,10 @@ def main():
             "check": check}
     if roofline_dense is not None:
         line["roofline_dense"] = roofline_dense
+        try:
+            line["other_configs"] = other_configs(device)
+        except Exception as e:                                   # informational block: never break the bench line
+            line["other_configs"] = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline and world == 1:
         n_s = 4096 if d >= 32 else 32768             # 10-30 s of CPU work on the box's host cores
         ns = 10
