@@ -752,7 +752,7 @@ static int run_prefactor_stream(sc_engine *e, int mode, cudaStream_t st) {
   none.imass = e->dev.q0;
   for (long long t0 = 0; t0 < n; t0 += ntb) {
     const int nt = (int)std::min<long long>(ntb, n - t0);
-    CU(launch_stream((int)std::min<long long>((long long)nt * L.ngroups, sm), e->dev, none, 0.0, 1, (int)t0, nt, A, L, st));
+    CU(launch_stream((long long)nt * L.ngroups, sm, e->dev, none, 0.0, 1, (int)t0, nt, A, L, st));
     if (dense) CU(launch_rmult(e->dev, nt, A.T, cm, sm, st));
     CU(launch_lu_batch(cm, dr, nt, det, sm, 0, st));
     k_track_only<<<(nt + 127) / 128, 128, 0, st>>>(e->dev, (int)t0, nt, det, mode == MODE_INIT ? 1 : 0);
@@ -876,7 +876,7 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
         e->launches += 1;
       }
       timing_mark(e, TS_RK4, st);
-      CU(launch_stream((int)std::min<long long>((long long)nt * L.ngroups, sm), e->dev, P, h, ks, (int)t0, nt, A, L, st));
+      CU(launch_stream((long long)nt * L.ngroups, sm, e->dev, P, h, ks, (int)t0, nt, A, L, st));
       if (dense) {
         timing_mark(e, TS_RMULT, st);
         CU(launch_rmult(e->dev, (long long)ks * nt, T, cm, sm, st));
@@ -896,9 +896,9 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   CU(cudaGetLastError());
   e->launches += 1;
   e->kernel_name = dense ? (dr > 64 ? "k_rk4_stream+k_rmult+k_lu_big+k_hk_finish"
-                                    : dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_batch+k_hk_finish")
+                                    : dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_warp+k_hk_finish")
                          : (dr > 64 ? "k_rk4_stream+k_lu_big+k_hk_finish"
-                                    : dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_batch+k_hk_finish");
+                                    : dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_warp+k_hk_finish");
   return SC_OK;
 }
 
@@ -906,9 +906,12 @@ static int run_hk_kernel(sc_engine *e, const PotDev &P, double h, int nsteps, in
                          bool allow_mma = true) {
   LaunchPlan pl;
   if (allow_mma && getenv("SC_NO_MMA")) allow_mma = false;  // diagnostics: force the DFMA kernel
-  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && !e->dense_engine && !getenv("SC_DENSE_ENGINE") && chunk_supported(e->dev, P))
+  // (the per-step snapshots of the fused Walton-Manolopoulos launches, d <= 16, are written by k_hk_small / k_hk_generic only)
+  const bool snapshots = e->dev.snap != nullptr;
+  if (allow_mma && !snapshots && mode == MODE_STEP && !getenv("SC_NO_CHUNK") && !e->dense_engine && !getenv("SC_DENSE_ENGINE") &&
+      chunk_supported(e->dev, P))
     return run_hk_chunked(e, P, h, nsteps, out_dev, st);
-  if (allow_mma && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
+  if (allow_mma && !snapshots && mode == MODE_STEP && !getenv("SC_NO_STREAM") && stream_supported(e->dev, P))
     return run_hk_stream(e, P, h, nsteps, out_dev, st);
   if (e->dev.d > 62) {                       // the set-up / read-out modes of k_hk_generic do not fit in shared memory
     if (mode == MODE_INIT || mode == MODE_TRACK) return run_prefactor_stream(e, mode, st);

@@ -251,7 +251,7 @@ extern "C" int sc_engine_stage_finish(sc_engine *e, double dt, void *stream) {
     PotDev P = PotDev();
     P.d = d;
     P.imass = im;
-    CU(launch_stream((int)std::min<long long>((long long)n * L.ngroups, sm), e->dev, P, dt, 1, 0, (int)n, A, L, st));
+    CU(launch_stream((long long)n * L.ngroups, sm, e->dev, P, dt, 1, 0, (int)n, A, L, st));
     if (dense) CU(launch_rmult(e->dev, (long long)n, A.T, cm, sm, st));
     CU(launch_lu_batch(cm, dr, (int)n, det, sm, 0, st));
     k_track_only<<<(int)((n + 127) / 128), 128, 0, st>>>(e->dev, 0, (int)n, det, 0);

@@ -1,5 +1,5 @@
 // sc_stream.cuh -- dense column pipeline: the Herman-Kluk step for ANY potential (per-trajectory dense Hessians) and ANY
-// width matrices (dense, rank deficient), 17 <= d <= 64.
+// width matrices (dense, rank deficient), 13 <= d <= 96 (d <= 64 for per-trajectory Hessians).
 //
 // Same structural facts as sc_chunk.cuh: the 2d columns of the monodromy blocks are independent linear ODEs driven by the
 // same Hessians (propagators.py:342-357), and the (q, p, S) path does not depend on the monodromy matrices.  The step is
@@ -73,9 +73,11 @@ struct StreamArgs {
 
 // ------------------------------------------------------------------ matrix kernel
 constexpr int stream_max_threads(int nk, int ntw) { return nk <= 16 ? 32 * ((nk + ntw - 1) / ntw) : 256; }
+// small systems leave most of the shared memory free: several CTAs (trajectories) per SM, registers capped accordingly
+constexpr int stream_min_ctas(int nk) { return nk <= 8 ? 4 : nk <= 10 ? 2 : 1; }
 
 template <int NK, int NTW>
-__global__ void __launch_bounds__(stream_max_threads(NK, NTW), 1)
+__global__ void __launch_bounds__(stream_max_threads(NK, NTW), stream_min_ctas(NK))
 k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, StreamArgs A, StreamLayout L) {
   constexpr int MT = (NK + 1) / 2;                    // 8-row tiles
   constexpr int LDH = cols_ldh(NK), DK = 4 * NK;
@@ -343,27 +345,37 @@ k_rk4_stream(EngDev E, PotDev P, double h, int nsteps, int traj0, int ntb, Strea
   (void)dr;
 }
 
+// work = CTAs' worth of items (trajectories x tile groups); the grid is one wave: SMs x resident CTAs of this instantiation
 template <int NK, int NTW>
-static cudaError_t launch_stream_t(int grid, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb,
-                                   const StreamArgs &A, const StreamLayout &L, cudaStream_t st) {
-  cudaError_t ce = cudaFuncSetAttribute(k_rk4_stream<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (ce != cudaSuccess) return ce;
-  k_rk4_stream<NK, NTW><<<grid, 32 * L.nwarp, smem, st>>>(E, P, h, nsteps, traj0, ntb, A, L);
+static cudaError_t launch_stream_t(long long work, int sm, size_t smem, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0,
+                                   int ntb, const StreamArgs &A, const StreamLayout &L, cudaStream_t st) {
+  static size_t occ_smem = ~(size_t)0;
+  static int occ = 1;
+  if (occ_smem != smem) {
+    cudaError_t ce = cudaFuncSetAttribute(k_rk4_stream<NK, NTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ce != cudaSuccess) return ce;
+    ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rk4_stream<NK, NTW>, 32 * L.nwarp, smem);
+    if (ce != cudaSuccess) return ce;
+    if (occ < 1) occ = 1;
+    occ_smem = smem;
+  }
+  const long long grid = work < (long long)sm * occ ? work : (long long)sm * occ;
+  k_rk4_stream<NK, NTW><<<(int)(grid < 1 ? 1 : grid), 32 * L.nwarp, smem, st>>>(E, P, h, nsteps, traj0, ntb, A, L);
   return cudaGetLastError();
 }
 
-static cudaError_t launch_stream(int grid, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb,
+static cudaError_t launch_stream(long long work, int sm, const EngDev &E, const PotDev &P, double h, int nsteps, int traj0, int ntb,
                                  const StreamArgs &A, const StreamLayout &L, cudaStream_t st) {
   const size_t smem = sizeof(double) * (size_t)L.total;
   switch (L.dk / 4) {
 #define SC_STREAM_CASE(N) \
-  case N: return launch_stream_t<N, 2>(grid, smem, E, P, h, nsteps, traj0, ntb, A, L, st);
-    SC_STREAM_CASE(5) SC_STREAM_CASE(6) SC_STREAM_CASE(7) SC_STREAM_CASE(8) SC_STREAM_CASE(9) SC_STREAM_CASE(10)
+  case N: return launch_stream_t<N, 2>(work, sm, smem, E, P, h, nsteps, traj0, ntb, A, L, st);
+    SC_STREAM_CASE(4) SC_STREAM_CASE(5) SC_STREAM_CASE(6) SC_STREAM_CASE(7) SC_STREAM_CASE(8) SC_STREAM_CASE(9) SC_STREAM_CASE(10)
     SC_STREAM_CASE(11) SC_STREAM_CASE(12) SC_STREAM_CASE(13) SC_STREAM_CASE(14) SC_STREAM_CASE(15) SC_STREAM_CASE(16)
 #undef SC_STREAM_CASE
     // 64 < d <= 96: one tile per warp, several CTAs (tile groups) per trajectory, each streaming the Hessians itself
 #define SC_STREAM_CASE1(N) \
-  case N: return launch_stream_t<N, 1>(grid, smem, E, P, h, nsteps, traj0, ntb, A, L, st);
+  case N: return launch_stream_t<N, 1>(work, sm, smem, E, P, h, nsteps, traj0, ntb, A, L, st);
     SC_STREAM_CASE1(17) SC_STREAM_CASE1(18) SC_STREAM_CASE1(19) SC_STREAM_CASE1(20) SC_STREAM_CASE1(21) SC_STREAM_CASE1(22)
     SC_STREAM_CASE1(23) SC_STREAM_CASE1(24)
 #undef SC_STREAM_CASE1
@@ -918,7 +930,7 @@ static cudaError_t launch_expand(const PotDev &P, int rot, int nsteps, int ntb, 
                                  cudaStream_t st) {
   switch ((P.d + 3) / 4) {
 #define SC_EXPAND_CASE(N) case N: return launch_expand_t<N>(P, rot, nsteps, ntb, hd, hs, sm_count, st);
-    SC_EXPAND_CASE(5) SC_EXPAND_CASE(6) SC_EXPAND_CASE(7) SC_EXPAND_CASE(8) SC_EXPAND_CASE(9) SC_EXPAND_CASE(10)
+    SC_EXPAND_CASE(4) SC_EXPAND_CASE(5) SC_EXPAND_CASE(6) SC_EXPAND_CASE(7) SC_EXPAND_CASE(8) SC_EXPAND_CASE(9) SC_EXPAND_CASE(10)
     SC_EXPAND_CASE(11) SC_EXPAND_CASE(12) SC_EXPAND_CASE(13) SC_EXPAND_CASE(14) SC_EXPAND_CASE(15) SC_EXPAND_CASE(16)
 #undef SC_EXPAND_CASE
     default: return cudaErrorInvalidValue;
@@ -1138,7 +1150,8 @@ k_corr_general(EngDev E, const double *__restrict__ R, const double *__restrict_
 }
 
 static bool stream_supported(const EngDev &E, const PotDev &P) {
-  if (E.d < 17 || E.d > SC_MAX_DIM) return false;
+  if (E.d < 13 || E.d > SC_MAX_DIM) return false;      // 13 .. 16: between the largest k_hk_small and the stage interface's limit
+  if (P.type == POT_GDML && E.d < 17) return false;    // the sGDML stream starts where the stage interface switches (d >= 17)
   if (P.type == POT_HARMONIC) return true;
   if (E.d > 64) return false;                  // Hessian expansion / sGDML kernels: d <= 64
   return P.type == POT_ROTATED_MORSE || P.type == POT_GDML || P.type == POT_MORSE || P.type == POT_NONHARMONIC;

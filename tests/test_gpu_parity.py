@@ -185,7 +185,7 @@ def test_wm_fused_propagate_matches_reference(name, cuda_device):
     _check_wm_signs(pr, g)
 
 
-@pytest.mark.parametrize("d,rotated", [(24, False), (24, True), (32, True), (60, False)])
+@pytest.mark.parametrize("d,rotated", [(14, False), (16, True), (24, False), (24, True), (32, True), (60, False)])
 def test_wm_at_larger_dimensions(d, rotated, cuda_device):
     """Walton-Manolopoulos beyond the small systems: a CTA per trajectory with the workspace in shared memory up to 29 modes
     (full-rank widths: 16 d^2 complex numbers), in global-memory slabs above (k_wm_global).  AS model with d modes
@@ -211,7 +211,7 @@ def test_wm_at_larger_dimensions(d, rotated, cuda_device):
     pr = propagators.WaltonManolopoulosPropagator(T(G), T(G), 500, 500, device=cuda_device)
     pr.set_ensemble(T(q0), T(p0), T(G), T(zi), T(probi))
     auto, ic = run_loop(pr, pot, dt, nt, m.en_zpt)
-    assert pr.kernel_name().endswith("k_wm_global" if d > 29 else "+k_wm")
+    assert pr.kernel_name().endswith("k_wm_global" if d > 29 else "+k_wm" if d > 16 else "+k_wm_fused")
     assert relerr(auto, ref['autocorrelation']) < TOL
     assert relerr(ic, ref['ic_correlation']) < TOL
     st = pr.sign_trackers
@@ -638,7 +638,7 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
 
 
 # ------------------------------------------------------------------ general path: dense Gamma, rank deficient
-@pytest.mark.parametrize("d", [23, 40, 54, 60, 64, 72, 96])
+@pytest.mark.parametrize("d", [13, 16, 23, 40, 54, 60, 64, 72, 96])
 def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on the dense column pipeline (sc_stream.cuh):
     Hessian and left prefactor factors streamed through the shared-memory ring, k_rmult for the right factors (k-padding at
@@ -723,7 +723,7 @@ def test_small_kernel_edge_shapes(d, n, nt, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
 
 
-@pytest.mark.parametrize("d,n,nt", [(17, 1, 4), (18, 2, 5), (31, 149, 4), (32, 3, 37), (33, 150, 3), (47, 297, 3), (61, 5, 4), (65, 7, 3),
+@pytest.mark.parametrize("d,n,nt", [(13, 5, 4), (14, 1, 3), (16, 150, 5), (17, 1, 4), (18, 2, 5), (31, 149, 4), (32, 3, 37), (33, 150, 3), (47, 297, 3), (61, 5, 4), (65, 7, 3),
                                     (80, 151, 3)])
 def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
     """ragged shapes of the dense column pipeline: smallest d, d not a multiple of 4 / 8, one or two trajectories (fewer than
@@ -749,7 +749,7 @@ def test_dense_pipeline_edge_shapes(d, n, nt, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref['signs'][0])
 
 
-@pytest.mark.parametrize("d", [20, 40])
+@pytest.mark.parametrize("d", [14, 20, 40])
 def test_separable_potential_with_dense_widths(d, cuda_device):
     """AS (Morse) potential -- diagonal Hessian -- with DENSE width matrices (a wavepacket whose widths are not aligned with the
     modes): k_path_separable + k_aux_terms + expanded diagonal Hessians + the dense prefactor stages, vs the C oracle"""
@@ -796,7 +796,7 @@ def test_rotated_models_run_on_the_stream_pipeline(name, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), g['signs_C'])
 
 
-@pytest.mark.parametrize("d", [20, 33, 60, 64])
+@pytest.mark.parametrize("d", [15, 20, 33, 60, 64])
 def test_dense_engine_option_on_separable_model(d, cuda_device):
     """AS model through the general dense pipeline (diagonal stage Hessians expanded to full matrices, option
     'dense_engine') vs the C oracle -- the configuration the dense-engine roofline of configs[3] is quoted on"""

@@ -22,5 +22,13 @@ a, i = pr.propagate(pot, dt, K, m['en_zpt'])
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); a, i = pr.propagate(pot, dt, K, m['en_zpt']); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
+if os.environ.get("SC_PROBE_SLOTS"):
+    from semiclassical_b200 import _native
+    kt = np.zeros(8)
+    _native.lib().sc_engine_set_timing(pr._engine, 1)
+    pr.propagate(pot, dt, K, m['en_zpt'])
+    torch.cuda.synchronize()
+    _native.lib().sc_engine_get_timing_slots(pr._engine, kt.ctypes.data, 8)
+    print("kernel_ms of the last launch: path %.2f rk4 %.2f rmult %.2f lu %.2f finish %.2f hess %.2f" % (kt[0], kt[1], kt[4], kt[2], kt[3], kt[5]))
 print(json.dumps({"workload": f"harmonic molecule-like, d={d}, d'={d-6}, dense Gamma", "ntraj": n, "steps": K, "ms": ms,
                   "traj_steps_per_s": n * K / ms * 1e3, "kernel": pr.kernel_name(), "C_last": [a[-1].real, a[-1].imag]}))
