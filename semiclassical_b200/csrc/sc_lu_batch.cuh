@@ -133,7 +133,7 @@ struct LuWarpStep<DRM, DRM, LPM> {
 };
 
 template <int DRM>
-__global__ void __launch_bounds__(128, (DRM <= 16 ? 4 : 2))
+__global__ void __launch_bounds__(128, (DRM <= 16 ? 4 : DRM <= 24 ? 3 : 2))
 k_lu_warp(const double2 *__restrict__ mats, int dr, int nmat, double2 *__restrict__ det_out) {
   constexpr int LPM = DRM <= 16 ? 16 : 32, MPW = 32 / LPM;       // lanes per matrix, matrices per warp
   __shared__ double2 lub[4 * MPW][2 * DRM];
