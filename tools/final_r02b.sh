@@ -6,3 +6,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02_fin
 bash tools/round2_configs.sh > gpurun_out/configs_bench_r02.jsonl 2> gpurun_out/configs_bench_r02.err
 python tools/wm_big_probe.py 24 4000 4 | tail -1 >> gpurun_out/configs_bench_r02.jsonl
 python tools/wm_big_probe.py 60 2368 2 | tail -1 >> gpurun_out/configs_bench_r02.jsonl
+bash tools/dim_sweep.sh > gpurun_out/dim_sweep_r02.jsonl 2> gpurun_out/dim_sweep_r02.err
