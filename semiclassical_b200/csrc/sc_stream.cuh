@@ -74,7 +74,7 @@ struct StreamArgs {
 // ------------------------------------------------------------------ matrix kernel
 constexpr int stream_max_threads(int nk, int ntw) { return nk <= 16 ? 32 * ((nk + ntw - 1) / ntw) : 256; }
 // small systems leave most of the shared memory free: several CTAs (trajectories) per SM, registers capped accordingly
-constexpr int stream_min_ctas(int nk) { return nk <= 8 ? 4 : nk <= 10 ? 2 : 1; }
+constexpr int stream_min_ctas(int nk) { return nk <= 6 ? 5 : nk <= 8 ? 4 : nk <= 10 ? 2 : 1; }
 
 template <int NK, int NTW>
 __global__ void __launch_bounds__(stream_max_threads(NK, NTW), stream_min_ctas(NK))
