@@ -896,9 +896,9 @@ static int run_hk_stream(sc_engine *e, const PotDev &P, double h, int nsteps, do
   CU(cudaGetLastError());
   e->launches += 1;
   e->kernel_name = dense ? (dr > 64 ? "k_rk4_stream+k_rmult+k_lu_big+k_hk_finish"
-                                    : dr > 32 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_warp+k_hk_finish")
+                                    : dr > 24 ? "k_rk4_stream+k_rmult+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_rmult+k_lu_warp+k_hk_finish")
                          : (dr > 64 ? "k_rk4_stream+k_lu_big+k_hk_finish"
-                                    : dr > 32 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_warp+k_hk_finish");
+                                    : dr > 24 ? "k_rk4_stream+k_lu_mma+k_hk_finish" : "k_rk4_stream+k_lu_warp+k_hk_finish");
   return SC_OK;
 }
 

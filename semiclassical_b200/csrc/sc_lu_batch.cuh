@@ -187,7 +187,11 @@ static cudaError_t launch_lu_batch(const double2 *mats, int dr, int nmat, double
     k_lu_big<<<grid, 256, smem, st>>>(mats, dr, nmat, det_out);
     return cudaGetLastError();
   }
-  if (dr > 32 && !getenv("SC_LU_DFMA")) {
+  // crossover measured on rotated AS models (d' = d, 148 000 x 16 matrices): d' = 24: k_lu_warp 47 ms / k_lu_mma 51 ms;
+  // d' = 26: 86 / 58; d' = 32: 114 / 70.  k_lu_mma wants exactly three CTAs per SM at every size (two: -25 %, four: -35 %)
+  int mma_min = 24;
+  if (const char *s = getenv("SC_LU_MMA_MIN")) mma_min = atoi(s);
+  if (dr > mma_min && !getenv("SC_LU_DFMA")) {
     // trailing updates on the FP64 tensor pipe (sc_lu_mma.cuh); 3 matrices per SM (60 KB of panels each at dr = 60)
     const size_t smem = lum_smem_bytes(dr);
     cudaError_t ce = cudaFuncSetAttribute(k_lu_mma<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

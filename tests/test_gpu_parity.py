@@ -638,11 +638,11 @@ def test_dynamics_driver_matches_reference_loop(tmp_path, cuda_device):
 
 
 # ------------------------------------------------------------------ general path: dense Gamma, rank deficient
-@pytest.mark.parametrize("d", [13, 16, 23, 40, 54, 60, 64, 72, 96])
+@pytest.mark.parametrize("d", [13, 16, 23, 30, 31, 38, 40, 54, 60, 64, 72, 96])
 def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     """dense Hessian + dense width matrices with 6 zero modes (d' = d - 6) on the dense column pipeline (sc_stream.cuh):
     Hessian and left prefactor factors streamed through the shared-memory ring, k_rmult for the right factors (k-padding at
-    d = 23), batched LU with d' = 17 (k_lu_batch), 34 (k_lu_mma, ragged last panel), 48, 54, 58"""
+    d = 23), batched LU with d' = 7, 10, 17, 24 (k_lu_warp), 25, 32, 34 (k_lu_mma, ragged last panel), 48, 54, 58"""
     from oracle import oracle
     from semiclassical_b200 import workloads, potentials, propagators
     m = workloads.harmonic_molecule_synthetic(d)
