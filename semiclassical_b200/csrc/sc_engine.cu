@@ -328,7 +328,10 @@ static int wm_setup(WMState &w, const sc_engine_config &cfg, DevPool &pool) {
     if (w.groups > 4) w.groups = 4;
     if (w.groups < 1) w.groups = 1;
   } else {
-    w.tpt = 128;
+    // one CTA per trajectory; above 16 modes the workspace leaves room for one CTA per SM only: 512 threads hide the latency
+    // of the shared-memory products that 128 cannot (16 of them per SM instead of 4 warps)
+    w.tpt = d <= 16 ? 128 : 512;
+    if (const char *s = getenv("SC_WM_TPT")) w.tpt = (atoi(s) == 512 || atoi(s) == 256) && d > 16 ? atoi(s) : 128;
     w.groups = 1;
   }
   w.smem = ws * w.groups;
@@ -393,6 +396,12 @@ static int wm_launch(WMState &w, const EngDev &D, int mode, double inv_norm, dou
   } else if (w.tpt == 32) {
     CU(cudaFuncSetAttribute(k_wm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
     k_wm<32><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
+  } else if (w.tpt == 512) {
+    CU(cudaFuncSetAttribute(k_wm<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<512><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
+  } else if (w.tpt == 256) {
+    CU(cudaFuncSetAttribute(k_wm<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+    k_wm<256><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);
   } else {
     CU(cudaFuncSetAttribute(k_wm<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
     k_wm<128><<<w.grid, threads, w.smem, st>>>(D, w.dev, w.L, mode, w.partials);

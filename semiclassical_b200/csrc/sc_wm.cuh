@@ -663,7 +663,7 @@ SC_HD void wm_trajectory(const EngDev &E, const WMDev &W, const WMLayout &L, dou
 
 #if defined(__CUDACC__)
 template <int TPT>
-__global__ void __launch_bounds__(128) k_wm(EngDev E, WMDev W, WMLayout L, int mode, double *partials) {
+__global__ void __launch_bounds__(TPT <= 128 ? 128 : TPT) k_wm(EngDev E, WMDev W, WMLayout L, int mode, double *partials) {
   extern __shared__ __align__(16) double2 wm_smem[];
   const int G = blockDim.x / TPT, gid = threadIdx.x / TPT, t = threadIdx.x % TPT;
   const int gg = blockIdx.x * G + gid, NG = gridDim.x * G;
