@@ -1,4 +1,4 @@
-// sc_small.cuh -- fused Herman-Kluk step kernel for small systems (d = 1..6, 8, 9, 12; any rank d' <= d): register-resident
+// sc_small.cuh -- fused Herman-Kluk step kernel for small systems (d <= 12; any rank d' <= d): register-resident
 // monodromy columns.
 //
 // k_hk_generic (sc_kernels.cuh) gives a whole warp to one trajectory and keeps its state in shared memory; at d = 5 that
@@ -466,7 +466,7 @@ inline bool small_supported(const EngDev &E, const PotDev &P) {
   if (!(P.type == POT_MORSE || P.type == POT_NONHARMONIC || P.type == POT_HARMONIC || P.type == POT_ROTATED_MORSE)) return false;
   if (E.diag && E.dr != E.d) return false;
   const int d = E.d;
-  return (d >= 1 && d <= 6) || d == 8 || d == 9 || d == 12;     // any rank d' <= d (zero-padded factors)
+  return d >= 1 && d <= 12;                                     // any rank d' <= d (zero-padded factors)
 }
 
 template <int D, int DR, int PT = -1, int DG = -1>
@@ -507,7 +507,7 @@ inline cudaError_t launch_small(int sm_count, const EngDev &E, const PotDev &P, 
 #define SC_SMALL_CASE(D_) \
   if (E.d == D_) return launch_small_t<D_, D_>(sm_count, E, P, h, nsteps, partials, nrows_groups, plan_only, st)
   SC_SMALL_CASE(1); SC_SMALL_CASE(2); SC_SMALL_CASE(3); SC_SMALL_CASE(4); SC_SMALL_CASE(5); SC_SMALL_CASE(6);
-  SC_SMALL_CASE(8); SC_SMALL_CASE(9); SC_SMALL_CASE(12);
+  SC_SMALL_CASE(7); SC_SMALL_CASE(8); SC_SMALL_CASE(9); SC_SMALL_CASE(10); SC_SMALL_CASE(11); SC_SMALL_CASE(12);
 #undef SC_SMALL_CASE
   return cudaErrorInvalidValue;
 }

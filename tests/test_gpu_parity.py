@@ -667,7 +667,7 @@ def test_dense_harmonic_molecule_against_oracle(d, cuda_device):
     assert np.array_equal(pr.sign_trackers["prefactorC"]["signs"].real.cpu().numpy(), ref2['signs'][0])
 
 
-@pytest.mark.parametrize("d,nzero", [(2, 0), (3, 1), (4, 2), (6, 0), (6, 3), (8, 2), (9, 3), (12, 5), (12, 0)])
+@pytest.mark.parametrize("d,nzero", [(2, 0), (3, 1), (4, 2), (6, 0), (6, 3), (7, 1), (8, 2), (9, 3), (10, 4), (11, 0), (12, 5), (12, 0)])
 def test_small_systems_any_rank(d, nzero, cuda_device):
     """k_hk_small with dense width matrices of rank d' = d - nzero <= d (the factors are zero-padded to d and the padded
     diagonal of the prefactor matrix set to one): dense harmonic 'molecules' with 2 ... 12 coordinates against the C oracle"""
