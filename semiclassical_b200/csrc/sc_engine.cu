@@ -679,7 +679,7 @@ static int run_hk_chunked(sc_engine *e, const PotDev &P, double h, int nsteps, d
   k_reduce_partials<<<nsteps, 160, 0, st>>>(e->partials, (int)ngroups, nsteps, 1.0 / (double)e->ntraj_norm, 1.0 / (double)n, out_dev);
   CU(cudaGetLastError());
   e->launches += 1;
-  e->kernel_name = "k_rk4_wcols+k_lu_mma+k_hk_finish";
+  e->kernel_name = d > 24 ? "k_rk4_wcols+k_lu_mma+k_hk_finish" : "k_rk4_wcols+k_lu_warp+k_hk_finish";
   return SC_OK;
 }
 

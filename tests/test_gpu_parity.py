@@ -439,10 +439,11 @@ def test_python_potential_at_d72(cuda_device):
 
 
 # ------------------------------------------------------------------ column-chunked headline path
-@pytest.mark.parametrize("d", [33, 40, 51, 60, 62, 63, 64])
+@pytest.mark.parametrize("d", [17, 18, 23, 24, 25, 32, 33, 40, 51, 60, 62, 63, 64])
 def test_chunked_path_against_oracle(d, cuda_device):
     """diagonal-Gamma AS models on the chunked RK4 + batched-LU path (sc_chunk.cuh) vs the C oracle: ragged batch
-    (n not a multiple of anything), two launches of KC steps, odd chunk widths (d = 51), 4 chunks (d = 62)"""
+    (n not a multiple of anything), two launches of KC steps, odd chunk widths (d = 51), 4 chunks (d = 62); from d = 17
+    (the smallest instantiation) through both LU kernels (d <= 24: k_lu_warp)"""
     from oracle import oracle
     from semiclassical_b200 import workloads, potentials, propagators
     m = workloads.as_synthetic(d)
@@ -457,7 +458,7 @@ def test_chunked_path_against_oracle(d, cuda_device):
     pr.set_ensemble(T(m.q0), T(m.p0), T(G), T(zi), T(probi))
     a0, i0 = pr.autocorrelation(m.en_zpt), pr.ic_correlation(pot, m.en_zpt)
     a, i = pr.propagate(pot, dt, nt - 1, m.en_zpt)
-    assert pr.kernel_name().startswith("k_rk4_")
+    assert pr.kernel_name().startswith("k_rk4_wcols+")
     assert relerr(np.concatenate(([a0], a)), ref['autocorrelation']) < TOL
     assert relerr(np.concatenate(([i0], i)), ref['ic_correlation']) < TOL
     # one more step through the drop-in API, then state / prefactor / branch signs of all trajectories
